@@ -1,0 +1,78 @@
+"""ctypes binding of libgramhead.so (C ABI: include/gramhead.h). There is no fallback: if the library is missing or a
+call fails, this raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_int, c_longlong, c_void_p, POINTER, c_uint
+
+from .build import LIB_PATH
+
+_LIB = None
+
+GH_DTYPE_F32 = 0
+GH_DTYPE_BF16 = 1
+GH_ERR_BAD_ARG = -1
+GH_ERR_UNSUPPORTED = -2
+
+_P = c_void_p
+_SIGNATURES = {
+    "gh_version": (c_int, []),
+    "gh_sm_count": (c_int, []),
+    "gh_last_device_error": (c_int, [POINTER(c_uint)]),
+    "gh_gram_pool_fwd": (c_int, [_P, c_int, c_longlong, c_longlong, c_int, c_int, c_int, c_int, _P, c_int, c_int,
+                                  c_int, c_int, _P]),
+    "gh_gram_dense_fwd": (c_int, [_P, c_int, c_longlong, c_longlong, c_int, c_int, c_int, _P, c_int, c_int, _P]),
+    "gh_adaptive_pool_fwd": (c_int, [_P, c_int, c_int, c_int, _P, c_int, c_int, _P]),
+    "gh_adaptive_pool_bwd": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "gh_gram_pool_bwd": (c_int, [_P, c_int, c_longlong, c_longlong, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P,
+                                  c_longlong, c_longlong, c_int, _P]),
+    "gh_gram_dense_bwd": (c_int, [_P, c_int, c_longlong, c_longlong, c_int, c_int, c_int, _P, _P, c_longlong,
+                                   c_longlong, c_int, _P]),
+    "gh_attn_head_fwd": (c_int, [_P] * 7 + [c_int] * 4 + [_P] * 5 + [_P]),
+    "gh_attn_head_bwd_workspace": (c_longlong, [c_int, c_int, c_int]),
+    "gh_attn_head_bwd": (c_int, [_P] * 10 + [c_int] * 4 + [_P] * 8 + [_P]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+class GramHeadError(RuntimeError):
+    pass
+
+
+def library_path() -> str:
+    return os.environ.get("GRAMHEAD_LIB", LIB_PATH)
+
+
+def lib() -> ctypes.CDLL:
+    """Loads the library once. Raises GramHeadError when it has not been built (python -m ...build)."""
+    global _LIB
+    if _LIB is None:
+        path = library_path()
+        if not os.path.isfile(path):
+            raise GramHeadError(
+                f"gramhead: {path} not found. Build it with `python -m heuristique_style_transfer_code_b200.build` "
+                "(needs nvcc, targets sm_100a). There is no CPU or PyTorch fallback for the Gram + attention head.")
+        handle = ctypes.CDLL(path)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = handle
+    return _LIB
+
+
+def check(code: int, what: str) -> None:
+    if code == 0:
+        return
+    if code == GH_ERR_BAD_ARG:
+        raise GramHeadError(f"gramhead: {what}: bad argument")
+    if code == GH_ERR_UNSUPPORTED:
+        raise GramHeadError(f"gramhead: {what}: shape not supported by this entry point")
+    raise GramHeadError(f"gramhead: {what}: CUDA error {code}")
+
+
+def last_device_error():
+    out = (c_uint * 4)()
+    rc = lib().gh_last_device_error(out)
+    return rc, tuple(out)

@@ -1,0 +1,369 @@
+// Batched symmetric Gram forward on tcgen05:  G_b = F_b F_b^T * scale,  F_b : C x HW (row-major, K = HW contiguous).
+//
+// Replaces TruncatedResNet50.gram_matrix (reference Models/Models_RESNET50_TRUNCATE_GRAM_with_Attention.py:26-30,
+// bmm + div(h*w)) and, in POOL mode, also the adaptive_avg_pool2d + stack/flatten that follow it (:51-55): the
+// C x C Gram only ever exists in TMEM; what reaches HBM is the g x g block-mean written straight into the
+// (B, L, g*g) descriptor buffer the attention consumes.
+//
+// Work decomposition
+//   unit      = (image b, 256x256 super-tile (I <= J) of the Gram, K-range kp of ksplit)
+//   CTA       = persistent, walks units blockIdx.x, +gridDim.x, ...
+//   warps 0-7 = producers: ld.global fp32/bf16 (coalesced along HW) -> cvt.rn.bf16x2 -> st.shared into the
+//               UMMA K-major SWIZZLE_128B layout (no separate cast pass over HBM, any HW, any pitch)
+//   warps 8-11= epilogue: tcgen05.ld -> in-register k x k block sums -> red.global.add into the descriptor
+//               (mirrored for off-diagonal 128-col blocks) or dense G stores
+//   warp 12   = TMEM owner + the single MMA-issuing thread
+//   smem ring = 6 stages of [256 rows][64 k] bf16 (32 KB). A diagonal super-tile consumes one stage per k-block
+//               (A and B tiles are the same rows), an off-diagonal one consumes two (I rows, then J rows).
+//   TMEM      = 512 columns: acc0 = rows 0-127 of I x 256 cols, acc1 = rows 128-255 of I x (128 | 256) cols.
+//               Only upper-triangle 128x128 blocks are ever issued: 3 of 4 on a diagonal super-tile.
+#pragma once
+#include "common.cuh"
+
+namespace gh {
+
+constexpr int kGfProducerWarps = 8;
+constexpr int kGfProducerThreads = kGfProducerWarps * 32;
+constexpr int kGfEpiWarp0 = 8;
+constexpr int kGfMmaWarp = 12;
+constexpr int kGfThreads = 13 * 32;
+constexpr int kGfStages = 6;
+constexpr uint32_t kGfStageRows = 256;
+constexpr uint32_t kGfStageBytes = kGfStageRows * kRowBytes;   // 32 KB
+constexpr uint32_t kGfSmemBytes = kGfStages * kGfStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t kGfTmemCols = 512;
+
+enum GramMode : int { GRAM_POOL = 0, GRAM_DENSE = 1 };
+
+struct GramFwdParams {
+  const void* F;
+  long long img_stride;   // elements between images
+  long long row_stride;   // elements between channel rows
+  int B, C, HW;
+  int nT;                 // ceil(C / 256)
+  int nST;                // nT (nT + 1) / 2 super-tiles per image
+  int ksplit;             // K partitions per super-tile
+  int nkb;                // ceil(HW / 64)
+  int total_units;
+  int g;                  // POOL: pooled size
+  float* out;             // POOL: (B, L, g*g) slice base for this stage; DENSE: (B, C, C)
+  long long out_img_stride;
+  float scale;
+  int use_atomics;        // DENSE only (POOL always accumulates with red.add into a zeroed buffer)
+};
+
+struct GramUnit {
+  int b, I, J, kb0, kb1;
+};
+
+__device__ __forceinline__ GramUnit gram_decode_unit(const GramFwdParams& p, int u) {
+  GramUnit w;
+  const int kp = u % p.ksplit;
+  int t = u / p.ksplit;
+  int st = t % p.nST;
+  w.b = t / p.nST;
+  int I = 0, rowlen = p.nT;
+  while (st >= rowlen) { st -= rowlen; ++I; --rowlen; }
+  w.I = I;
+  w.J = I + st;
+  w.kb0 = (int)(((long long)p.nkb * kp) / p.ksplit);
+  w.kb1 = (int)(((long long)p.nkb * (kp + 1)) / p.ksplit);
+  return w;
+}
+
+// ---- producers ----------------------------------------------------------------------------------------------------
+// One stage = rows [blk*256, blk*256+256) x k in [kb*64, kb*64+64). fp32 source, 16 B aligned rows.
+// 16 threads cover one row (64 fp32 = 256 B, one float4 each); a warp covers two rows per pass; 16 passes.
+__device__ __forceinline__ void gram_fill_stage_f32_vec(const GramFwdParams& p, int b, int blk, int kb, uint32_t stage_smem,
+                                                        int tid) {
+  const int half = tid >> 4, q = tid & 15;
+  const int k = kb * 64 + q * 4;
+  const bool kvalid = k < p.HW;   // HW % 4 == 0 on this path, so k+3 < HW too
+  const float* base = reinterpret_cast<const float*>(p.F) + (long long)b * p.img_stride + k;
+  const int c0 = blk * 256 + half;
+  float4 v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = c0 + i * 16;
+    if (kvalid && c < p.C) v[i] = ldg_stream_f4(base + (long long)c * p.row_stride);
+    else v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const uint32_t r = (uint32_t)(half + i * 16);
+    sts_u2(stage_smem + sw128_off(r, (uint32_t)(q * 4)), pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
+  }
+}
+// Any HW / pitch / alignment: scalar loads with per-element bounds.
+__device__ __forceinline__ void gram_fill_stage_f32_scalar(const GramFwdParams& p, int b, int blk, int kb,
+                                                           uint32_t stage_smem, int tid) {
+  const int half = tid >> 4, q = tid & 15;
+  const int k = kb * 64 + q * 4;
+  const float* base = reinterpret_cast<const float*>(p.F) + (long long)b * p.img_stride + k;
+  const int c0 = blk * 256 + half;
+#pragma unroll 4
+  for (int i = 0; i < 16; ++i) {
+    const int c = c0 + i * 16;
+    float x[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c < p.C) {
+      const float* rp = base + (long long)c * p.row_stride;
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (k + e < p.HW) x[e] = __ldg(rp + e);
+    }
+    const uint32_t r = (uint32_t)(half + i * 16);
+    sts_u2(stage_smem + sw128_off(r, (uint32_t)(q * 4)), pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]));
+  }
+}
+// bf16 source, rows 8 B aligned (HW % 4 == 0): same thread map, 8 B per thread.
+__device__ __forceinline__ void gram_fill_stage_bf16_vec(const GramFwdParams& p, int b, int blk, int kb,
+                                                         uint32_t stage_smem, int tid) {
+  const int half = tid >> 4, q = tid & 15;
+  const int k = kb * 64 + q * 4;
+  const bool kvalid = k < p.HW;
+  const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(p.F) + (long long)b * p.img_stride + k;
+  const int c0 = blk * 256 + half;
+  uint2 v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = c0 + i * 16;
+    if (kvalid && c < p.C) v[i] = ldg_stream_u2(base + (long long)c * p.row_stride);
+    else v[i] = make_uint2(0u, 0u);
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const uint32_t r = (uint32_t)(half + i * 16);
+    sts_u2(stage_smem + sw128_off(r, (uint32_t)(q * 4)), v[i].x, v[i].y);
+  }
+}
+__device__ __forceinline__ void gram_fill_stage_bf16_scalar(const GramFwdParams& p, int b, int blk, int kb,
+                                                            uint32_t stage_smem, int tid) {
+  const int half = tid >> 4, q = tid & 15;
+  const int k = kb * 64 + q * 4;
+  const unsigned short* base = reinterpret_cast<const unsigned short*>(p.F) + (long long)b * p.img_stride + k;
+  const int c0 = blk * 256 + half;
+#pragma unroll 4
+  for (int i = 0; i < 16; ++i) {
+    const int c = c0 + i * 16;
+    unsigned int x[4] = {0u, 0u, 0u, 0u};
+    if (c < p.C) {
+      const unsigned short* rp = base + (long long)c * p.row_stride;
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (k + e < p.HW) x[e] = __ldg(rp + e);
+    }
+    const uint32_t r = (uint32_t)(half + i * 16);
+    sts_u2(stage_smem + sw128_off(r, (uint32_t)(q * 4)), x[0] | (x[1] << 16), x[2] | (x[3] << 16));
+  }
+}
+
+// ---- epilogue -----------------------------------------------------------------------------------------------------
+// One 32-lane x 32-column chunk of an accumulator. Thread = Gram row c_row, v[j] = G[c_row][c_col0 + j] (unscaled).
+template <int KP>
+__device__ __forceinline__ void gram_epi_pool_chunk(const float (&v)[32], int c_row, int c_col0, int C, int g,
+                                                    float scale, float* __restrict__ outp, bool mirror, int lane) {
+  constexpr int CW = KP < 32 ? KP : 32;   // columns summed in-thread per value
+  constexpr int NC = 32 / CW;             // values this chunk yields per row
+  constexpr int LK = KP < 32 ? KP : 32;   // rows (lanes) summed by shuffles
+  float s[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    float a = 0.f;
+#pragma unroll
+    for (int i = 0; i < CW; ++i) a += v[j * CW + i];
+    s[j] = a;
+  }
+#pragma unroll
+  for (int off = 1; off < LK; off <<= 1) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) s[j] += __shfl_xor_sync(0xffffffffu, s[j], off);
+  }
+  // Rows/cols >= C were zero-filled by the producers, so the sums need no masks; only the writes do.
+  const int lj = lane & (LK - 1);
+  const int pi = c_row / KP;
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    if ((j % LK) == lj && c_row < C) {
+      const int col = c_col0 + j * CW;
+      if (col < C) {
+        const int pj = col / KP;
+        const float val = s[j] * scale;
+        red_add_f32(outp + pi * g + pj, val);
+        if (mirror) red_add_f32(outp + pj * g + pi, val);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void gram_epi_dense_chunk(const float (&v)[32], int c_row, int c_col0, int C, float scale,
+                                                     float* __restrict__ G, bool mirror, bool atomics) {
+  if (c_row >= C) return;
+  float* rowp = G + (long long)c_row * C + c_col0;
+  if (!atomics && c_col0 + 32 <= C && (C & 3) == 0) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+      *reinterpret_cast<float4*>(rowp + j) = make_float4(v[j] * scale, v[j + 1] * scale, v[j + 2] * scale, v[j + 3] * scale);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (c_col0 + j < C) {
+        if (atomics) red_add_f32(rowp + j, v[j] * scale);
+        else rowp[j] = v[j] * scale;
+      }
+  }
+  if (mirror) {
+    // lanes = consecutive c_row -> each j is one coalesced 128 B store across the warp
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (c_col0 + j < C) {
+        float* mp = G + (long long)(c_col0 + j) * C + c_row;
+        if (atomics) red_add_f32(mp, v[j] * scale);
+        else *mp = v[j] * scale;
+      }
+  }
+}
+
+// SRC: 0 = fp32 vector, 1 = fp32 scalar, 2 = bf16 vector, 3 = bf16 scalar.  KP = pool factor (POOL) or 0 (DENSE).
+template <int SRC, int KP>
+__global__ void __launch_bounds__(kGfThreads, 1) gram_fwd_kernel(const GramFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = smem_base + kGfStages * kGfStageBytes;
+  // barrier map (8 B each): full[6], empty[6], tmem_full, tmem_empty, then the TMEM base word
+  const uint32_t bar_full = bars, bar_empty = bars + 8 * kGfStages;
+  const uint32_t bar_tfull = bars + 16 * kGfStages, bar_tempty = bar_tfull + 8;
+  const uint32_t tmem_slot = bar_tempty + 8;
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kGfStages; ++s) {
+      mbar_init(bar_full + 8 * s, kGfProducerWarps);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_tfull, 1);
+    mbar_init(bar_tempty, 4);
+    mbar_fence_init();
+  }
+  if (warp == kGfMmaWarp) tmem_alloc(tmem_slot, kGfTmemCols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp < kGfProducerWarps) {
+    // =========================== producers ===========================
+    uint32_t stage = 0, phase = 0;
+    for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+      const GramUnit w = gram_decode_unit(p, u);
+      const int nblk = (w.I == w.J) ? 1 : 2;
+      for (int kb = w.kb0; kb < w.kb1; ++kb) {
+        for (int h = 0; h < nblk; ++h) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1u, 100u + stage);
+          const uint32_t st_smem = smem_base + stage * kGfStageBytes;
+          const int blk = h == 0 ? w.I : w.J;
+          if (SRC == 0) gram_fill_stage_f32_vec(p, w.b, blk, kb, st_smem, threadIdx.x);
+          else if (SRC == 1) gram_fill_stage_f32_scalar(p, w.b, blk, kb, st_smem, threadIdx.x);
+          else if (SRC == 2) gram_fill_stage_bf16_vec(p, w.b, blk, kb, st_smem, threadIdx.x);
+          else gram_fill_stage_bf16_scalar(p, w.b, blk, kb, st_smem, threadIdx.x);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_full + 8 * stage);
+          if (++stage == kGfStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == kGfMmaWarp) {
+    // =========================== MMA issuer ===========================
+    uint32_t stage = 0, phase = 0, acc_phase = 0;
+    const uint32_t idesc256 = make_idesc_bf16(128, 256), idesc128 = make_idesc_bf16(128, 128);
+    for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+      const GramUnit w = gram_decode_unit(p, u);
+      const bool diag = (w.I == w.J);
+      mbar_wait(bar_tempty, acc_phase ^ 1u, 200u);   // epilogue has drained the previous unit's accumulators
+      tc_fence_after_sync();
+      for (int kb = w.kb0; kb < w.kb1; ++kb) {
+        const uint32_t sA = stage;
+        mbar_wait(bar_full + 8 * sA, phase, 300u + sA);
+        uint32_t sB = sA, phaseB = phase;
+        if (!diag) {
+          sB = sA + 1;
+          if (sB == kGfStages) { sB = 0; phaseB ^= 1u; }
+          mbar_wait(bar_full + 8 * sB, phaseB, 310u + sB);
+        }
+        tc_fence_after_sync();
+        if (lane == 0) {
+          const uint32_t aI = smem_base + sA * kGfStageBytes;   // rows of block I
+          const uint32_t aJ = smem_base + sB * kGfStageBytes;   // rows of block J (== I on the diagonal)
+          const uint32_t acc = (kb > w.kb0) ? 1u : 0u;
+#pragma unroll
+          for (uint32_t ks = 0; ks < kTileK / kUmmaK; ++ks) {
+            const uint32_t koff = ks * 32u;
+            // acc0: I rows 0-127 x J rows 0-255
+            umma_bf16(tmem_base + 0u, make_smem_desc_sw128(aI + koff), make_smem_desc_sw128(aJ + koff), idesc256,
+                      acc | ks);
+            if (diag) {
+              // acc1: I rows 128-255 x I rows 128-255 (the lower-left 128x128 block is never computed)
+              umma_bf16(tmem_base + 256u, make_smem_desc_sw128(aI + 128u * kRowBytes + koff),
+                        make_smem_desc_sw128(aI + 128u * kRowBytes + koff), idesc128, acc | ks);
+            } else {
+              // acc1: I rows 128-255 x J rows 0-255
+              umma_bf16(tmem_base + 256u, make_smem_desc_sw128(aI + 128u * kRowBytes + koff),
+                        make_smem_desc_sw128(aJ + koff), idesc256, acc | ks);
+            }
+          }
+          umma_commit(bar_empty + 8 * sA);
+          if (!diag) umma_commit(bar_empty + 8 * sB);
+          if (kb + 1 == w.kb1) umma_commit(bar_tfull);
+        }
+        __syncwarp();
+        stage = sB + 1; phase = phaseB;
+        if (stage == kGfStages) { stage = 0; phase ^= 1u; }
+      }
+      acc_phase ^= 1u;
+    }
+  } else {
+    // =========================== epilogue ===========================
+    const int q = warp - kGfEpiWarp0;   // TMEM lane quarter this warp may read (= warp % 4)
+    uint32_t acc_phase = 0;
+    for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+      const GramUnit w = gram_decode_unit(p, u);
+      const bool diag = (w.I == w.J);
+      mbar_wait(bar_tfull, acc_phase, 400u);
+      tc_fence_after_sync();
+      float* outp = p.out + (long long)w.b * p.out_img_stride;
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int a = 0; a < 2; ++a) {
+        const int c_row = w.I * 256 + a * 128 + q * 32 + lane;
+        const int ncols = (a == 1 && diag) ? 128 : 256;
+        const int colbase = w.J * 256 + ((a == 1 && diag) ? 128 : 0);
+#pragma unroll 1
+        for (int n0 = 0; n0 < ncols; n0 += 32) {
+          float v[32];
+          tmem_ld32(lane_addr + (uint32_t)(a * 256 + n0), v);
+          const int c_col0 = colbase + n0;
+          // a 128x128 block strictly above the diagonal is mirrored; diagonal blocks are complete on their own
+          const bool mirror = (c_col0 >> 7) > (c_row >> 7);
+          if (KP > 0) gram_epi_pool_chunk<(KP > 0 ? KP : 1)>(v, c_row, c_col0, p.C, p.g, p.scale, outp, mirror, lane);
+          else gram_epi_dense_chunk(v, c_row, c_col0, p.C, p.scale, outp, mirror, p.use_atomics != 0);
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty);
+      acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kGfMmaWarp) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, kGfTmemCols);
+  }
+}
+
+}  // namespace gh

@@ -1,0 +1,355 @@
+// libgramhead.so - host launchers behind the C ABI in include/gramhead.h. One translation unit:
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -Xcompiler -fPIC -shared gramhead.cu -o libgramhead.so
+#include "../../include/gramhead.h"
+#include "common.cuh"
+#include "gram_fwd.cuh"
+#include "gram_bwd.cuh"
+#include "attn_head.cuh"
+
+namespace gh {
+
+static int sm_count_cached() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+static int ilog2_exact(int v) {
+  if (v <= 0 || (v & (v - 1))) return -1;
+  int s = 0;
+  while ((1 << s) < v) ++s;
+  return s;
+}
+
+// K-split that best fills `ctas` persistent CTAs: minimise ceil(units/ctas) / (units/ctas), keep >= 4 k-blocks a part.
+static int choose_ksplit(long long base_units, int nkb, int ctas) {
+  int best = 1;
+  double best_eff = 0.0;
+  const int kmax = nkb / 4 > 1 ? nkb / 4 : 1;
+  for (int ks = 1; ks <= kmax && ks <= 16; ++ks) {
+    const double units = (double)base_units * ks;
+    const double waves = units / ctas;
+    const double eff = waves / (double)((long long)((units + ctas - 1) / ctas));
+    if (eff > best_eff + 0.02) { best_eff = eff; best = ks; }
+  }
+  return best;
+}
+
+template <int SRC>
+static cudaError_t launch_gram_fwd_kp(const GramFwdParams& p, int kp, int grid, cudaStream_t st) {
+#define GH_LAUNCH_GF(KP)                                                                                        \
+  {                                                                                                             \
+    cudaError_t e = cudaFuncSetAttribute(gram_fwd_kernel<SRC, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)kGfSmemBytes);                                                    \
+    if (e != cudaSuccess) return e;                                                                             \
+    gram_fwd_kernel<SRC, KP><<<grid, kGfThreads, kGfSmemBytes, st>>>(p);                                        \
+    return cudaGetLastError();                                                                                  \
+  }
+  switch (kp) {
+    case 0: GH_LAUNCH_GF(0)
+    case 1: GH_LAUNCH_GF(1)
+    case 2: GH_LAUNCH_GF(2)
+    case 4: GH_LAUNCH_GF(4)
+    case 8: GH_LAUNCH_GF(8)
+    case 16: GH_LAUNCH_GF(16)
+    case 32: GH_LAUNCH_GF(32)
+    case 64: GH_LAUNCH_GF(64)
+    case 128: GH_LAUNCH_GF(128)
+    default: return cudaErrorInvalidValue;
+  }
+#undef GH_LAUNCH_GF
+}
+
+static int gram_fwd_common(const void* F, int f_dtype, long long img_stride, long long row_stride, int B, int C, int HW,
+                           int mode, int g, float* out, long long out_img_stride, int ksplit, int max_ctas,
+                           cudaStream_t st) {
+  if (!F || !out || B <= 0 || C <= 0 || HW <= 0) return GH_ERR_BAD_ARG;
+  if (f_dtype != GH_DTYPE_F32 && f_dtype != GH_DTYPE_BF16) return GH_ERR_BAD_ARG;
+  int kp = 0;
+  if (mode == GRAM_POOL) {
+    if (g <= 0 || C % g != 0) return GH_ERR_UNSUPPORTED;
+    kp = C / g;
+    if (ilog2_exact(kp) < 0 || kp > 128) return GH_ERR_UNSUPPORTED;
+  }
+  GramFwdParams p;
+  p.F = F; p.img_stride = img_stride; p.row_stride = row_stride;
+  p.B = B; p.C = C; p.HW = HW;
+  p.nT = (C + 255) / 256;
+  p.nST = p.nT * (p.nT + 1) / 2;
+  p.nkb = (HW + 63) / 64;
+  const int sms = sm_count_cached();
+  const int ctas = (max_ctas > 0 && max_ctas < sms) ? max_ctas : sms;
+  const long long base_units = (long long)B * p.nST;
+  if (ksplit <= 0) ksplit = choose_ksplit(base_units, p.nkb, ctas);
+  if (ksplit > p.nkb) ksplit = p.nkb;
+  p.ksplit = ksplit;
+  const long long total = base_units * ksplit;
+  if (total > 0x7fffffffLL) return GH_ERR_UNSUPPORTED;
+  p.total_units = (int)total;
+  p.g = g; p.out = out; p.out_img_stride = out_img_stride;
+  p.scale = (mode == GRAM_POOL) ? 1.0f / ((float)HW * (float)kp * (float)kp) : 1.0f / (float)HW;
+  p.use_atomics = (ksplit > 1) ? 1 : 0;
+
+  cudaError_t e;
+  if (mode == GRAM_POOL) {
+    e = cudaMemset2DAsync(out, (size_t)out_img_stride * 4, 0, (size_t)g * g * 4, (size_t)B, st);
+    if (e != cudaSuccess) return (int)e;
+  } else if (p.use_atomics) {
+    e = cudaMemsetAsync(out, 0, (size_t)B * C * C * 4, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  const int grid = (int)(total < ctas ? total : ctas);
+  const uintptr_t addr = (uintptr_t)F;
+  const bool s4 = (HW % 4 == 0) && (row_stride % 4 == 0) && (img_stride % 4 == 0);
+  if (f_dtype == GH_DTYPE_F32) {
+    if (s4 && addr % 16 == 0) e = launch_gram_fwd_kp<0>(p, kp, grid, st);
+    else e = launch_gram_fwd_kp<1>(p, kp, grid, st);
+  } else {
+    if (s4 && addr % 8 == 0) e = launch_gram_fwd_kp<2>(p, kp, grid, st);
+    else e = launch_gram_fwd_kp<3>(p, kp, grid, st);
+  }
+  return (int)e;
+}
+
+static int gram_bwd_common(const void* F, int f_dtype, long long img_stride, long long row_stride, int B, int C, int HW,
+                           int mode, int g, const float* dP, long long dp_img_stride, const float* dG, float* dF,
+                           long long df_img_stride, long long df_row_stride, int max_ctas, cudaStream_t st) {
+  if (!F || !dF || B <= 0 || C <= 0 || HW <= 0) return GH_ERR_BAD_ARG;
+  if (f_dtype != GH_DTYPE_F32 && f_dtype != GH_DTYPE_BF16) return GH_ERR_BAD_ARG;
+  if (C % 16 != 0) return GH_ERR_UNSUPPORTED;
+  GramBwdParams p;
+  p.F = F; p.img_stride = img_stride; p.row_stride = row_stride;
+  p.B = B; p.C = C; p.HW = HW; p.mode = mode;
+  p.dP = dP; p.dp_img_stride = dp_img_stride; p.g = g; p.kshift = 0; p.dG = dG;
+  if (mode == GRAM_POOL) {
+    if (!dP) return GH_ERR_BAD_ARG;
+    if (g <= 0 || g > kGbMaxG || C % g != 0) return GH_ERR_UNSUPPORTED;
+    const int k = C / g;
+    p.kshift = ilog2_exact(k);
+    if (p.kshift < 0) return GH_ERR_UNSUPPORTED;
+    p.scale = 1.0f / ((float)HW * (float)k * (float)k);
+  } else {
+    if (!dG) return GH_ERR_BAD_ARG;
+    p.scale = 1.0f / (float)HW;
+  }
+  p.dF = dF; p.df_img_stride = df_img_stride; p.df_row_stride = df_row_stride;
+  p.NB = (C > 256) ? 2 : 1;
+  p.nHT = (HW + 127) / 128;
+  p.nCB = (C + 256 * p.NB - 1) / (256 * p.NB);
+  p.nkb = (C + 63) / 64;
+  p.stage_bytes = kGbATileBytes + (uint32_t)p.NB * kGbBBlkBytes;
+  p.stages = (int)(kGbRingBytes / p.stage_bytes);
+  if (p.stages > kGbMaxStages) p.stages = kGbMaxStages;
+  p.nacc = (p.NB == 1) ? 2 : 1;
+  const long long total = (long long)B * p.nHT * p.nCB;
+  if (total > 0x7fffffffLL) return GH_ERR_UNSUPPORTED;
+  p.total_units = (int)total;
+  const int sms = sm_count_cached();
+  const int ctas = (max_ctas > 0 && max_ctas < sms) ? max_ctas : sms;
+  const int grid = (int)(total < ctas ? total : ctas);
+  cudaError_t e;
+  if (f_dtype == GH_DTYPE_F32) {
+    e = cudaFuncSetAttribute(gram_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGbSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    gram_bwd_kernel<0><<<grid, kGbThreads, kGbSmemBytes, st>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(gram_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGbSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    gram_bwd_kernel<2><<<grid, kGbThreads, kGbSmemBytes, st>>>(p);
+  }
+  return (int)cudaGetLastError();
+}
+
+// ---- general-bin adaptive pooling (torch rule), used when C % g != 0 ------------------------------------------------
+__device__ __forceinline__ int bin_start(int i, int C, int g) { return (int)(((long long)i * C) / g); }
+__device__ __forceinline__ int bin_end(int i, int C, int g) { return (int)((((long long)(i + 1)) * C + g - 1) / g); }
+
+// grid (g, B), 256 threads: block (i, b) produces row i of the pooled matrix.
+__global__ void adaptive_pool_fwd_kernel(const float* __restrict__ G, int C, int g, float* __restrict__ desc,
+                                         long long desc_img_stride) {
+  const int i = blockIdx.x, b = blockIdx.y;
+  const int r0 = bin_start(i, C, g), r1 = bin_end(i, C, g);
+  const float* Gb = G + (long long)b * C * C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = warp; j < g; j += 8) {
+    const int c0 = bin_start(j, C, g), c1 = bin_end(j, C, g);
+    const int w = c1 - c0, n = (r1 - r0) * w;
+    float s = 0.f;
+    for (int t = lane; t < n; t += 32) s += Gb[(long long)(r0 + t / w) * C + c0 + t % w];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) desc[(long long)b * desc_img_stride + i * g + j] = s / (float)n;
+  }
+}
+// grid (ceil(C*C/256), B): one thread per dG element; sums the (at most 2x2) bins that contain (c, d).
+__global__ void adaptive_pool_bwd_kernel(const float* __restrict__ d_desc, long long desc_img_stride, int C, int g,
+                                         float* __restrict__ dG) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)C * C) return;
+  const int b = blockIdx.y;
+  const int c = (int)(idx / C), d = (int)(idx % C);
+  const float* dp = d_desc + (long long)b * desc_img_stride;
+  // bins containing c: i in [ilo, ihi]; start(i) <= c < end(i)
+  int ilo = (int)(((long long)c * g) / C);
+  while (ilo > 0 && bin_end(ilo - 1, C, g) > c) --ilo;
+  int jlo = (int)(((long long)d * g) / C);
+  while (jlo > 0 && bin_end(jlo - 1, C, g) > d) --jlo;
+  float s = 0.f;
+  for (int i = ilo; i < g && bin_start(i, C, g) <= c; ++i) {
+    if (bin_end(i, C, g) <= c) continue;
+    const float ni = (float)(bin_end(i, C, g) - bin_start(i, C, g));
+    for (int j = jlo; j < g && bin_start(j, C, g) <= d; ++j) {
+      if (bin_end(j, C, g) <= d) continue;
+      const float nj = (float)(bin_end(j, C, g) - bin_start(j, C, g));
+      s += dp[i * g + j] / (ni * nj);
+    }
+  }
+  dG[(long long)b * C * C + idx] = s;
+}
+
+}  // namespace gh
+
+using namespace gh;
+
+extern "C" {
+
+int gh_version(void) { return 100; }
+
+int gh_sm_count(void) { return sm_count_cached(); }
+
+int gh_last_device_error(unsigned int* out4) {
+  if (!out4) return GH_ERR_BAD_ARG;
+  cudaError_t e = cudaMemcpyFromSymbol(out4, g_dev_error, sizeof(unsigned int) * 4);
+  if (e != cudaSuccess) return (int)e;
+  unsigned int z[4] = {0, 0, 0, 0};
+  e = cudaMemcpyToSymbol(g_dev_error, z, sizeof(z));
+  return (int)e;
+}
+
+int gh_gram_pool_fwd(const void* F, int f_dtype, long long img_stride, long long row_stride, int B, int C, int HW,
+                     int g, float* desc, int l, int L, int ksplit, int max_ctas, void* stream) {
+  if (!desc || l < 0 || l >= L || g <= 0) return GH_ERR_BAD_ARG;
+  return gram_fwd_common(F, f_dtype, img_stride, row_stride, B, C, HW, GRAM_POOL, g, desc + (long long)l * g * g,
+                         (long long)L * g * g, ksplit, max_ctas, (cudaStream_t)stream);
+}
+
+int gh_gram_dense_fwd(const void* F, int f_dtype, long long img_stride, long long row_stride, int B, int C, int HW,
+                      float* G, int ksplit, int max_ctas, void* stream) {
+  return gram_fwd_common(F, f_dtype, img_stride, row_stride, B, C, HW, GRAM_DENSE, 0, G, (long long)C * C, ksplit,
+                         max_ctas, (cudaStream_t)stream);
+}
+
+int gh_adaptive_pool_fwd(const float* G, int B, int C, int g, float* desc, int l, int L, void* stream) {
+  if (!G || !desc || B <= 0 || C <= 0 || g <= 0 || l < 0 || l >= L) return GH_ERR_BAD_ARG;
+  if (B > 65535) return GH_ERR_UNSUPPORTED;
+  adaptive_pool_fwd_kernel<<<dim3(g, B), 256, 0, (cudaStream_t)stream>>>(G, C, g, desc + (long long)l * g * g,
+                                                                         (long long)L * g * g);
+  return (int)cudaGetLastError();
+}
+
+int gh_adaptive_pool_bwd(const float* d_desc, int l, int L, int B, int C, int g, float* dG, void* stream) {
+  if (!dG || !d_desc || B <= 0 || C <= 0 || g <= 0 || l < 0 || l >= L) return GH_ERR_BAD_ARG;
+  if (B > 65535) return GH_ERR_UNSUPPORTED;
+  const long long n = (long long)C * C;
+  adaptive_pool_bwd_kernel<<<dim3((unsigned)((n + 255) / 256), B), 256, 0, (cudaStream_t)stream>>>(
+      d_desc + (long long)l * g * g, (long long)L * g * g, C, g, dG);
+  return (int)cudaGetLastError();
+}
+
+int gh_gram_pool_bwd(const void* F, int f_dtype, long long img_stride, long long row_stride, int B, int C, int HW,
+                     int g, const float* d_desc, int l, int L, float* dF, long long df_img_stride,
+                     long long df_row_stride, int max_ctas, void* stream) {
+  if (!d_desc || l < 0 || l >= L || g <= 0) return GH_ERR_BAD_ARG;
+  return gram_bwd_common(F, f_dtype, img_stride, row_stride, B, C, HW, GRAM_POOL, g, d_desc + (long long)l * g * g,
+                         (long long)L * g * g, nullptr, dF, df_img_stride, df_row_stride, max_ctas,
+                         (cudaStream_t)stream);
+}
+
+int gh_gram_dense_bwd(const void* F, int f_dtype, long long img_stride, long long row_stride, int B, int C, int HW,
+                      const float* dG, float* dF, long long df_img_stride, long long df_row_stride, int max_ctas,
+                      void* stream) {
+  return gram_bwd_common(F, f_dtype, img_stride, row_stride, B, C, HW, GRAM_DENSE, 0, nullptr, 0, dG, dF,
+                         df_img_stride, df_row_stride, max_ctas, (cudaStream_t)stream);
+}
+
+int gh_attn_head_fwd(const float* desc, const float* W_in, const float* b_in, const float* W_out, const float* b_out,
+                     const float* W_c, const float* b_c, int B, int L, int E, int nc, float* qkv, float* probs,
+                     float* obar, float* emb, float* logits, void* stream) {
+  if (!desc || !W_in || !W_out || !W_c || !qkv || !probs || !obar || !emb || !logits) return GH_ERR_BAD_ARG;
+  if (B <= 0 || L <= 0 || E <= 0 || nc <= 0) return GH_ERR_BAD_ARG;
+  if (L > kMaxL) return GH_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e;
+  // QKV = X W_in^T + b_in           (B*L, 3E)
+  e = launch_sgemm(desc, E, 1, W_in, 1, E, b_in, qkv, 3LL * E, B * L, 3 * E, E, 0, st);
+  if (e != cudaSuccess) return (int)e;
+  attn_core_fwd_kernel<<<B, 128, 0, st>>>(qkv, probs, obar, L, E);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  // emb = Obar W_out^T + b_out      (B, E)
+  e = launch_sgemm(obar, E, 1, W_out, 1, E, b_out, emb, E, B, E, E, 0, st);
+  if (e != cudaSuccess) return (int)e;
+  // logits = emb W_c^T + b_c        (B, nc)
+  e = launch_sgemm(emb, E, 1, W_c, 1, E, b_c, logits, nc, B, nc, E, 0, st);
+  return (int)e;
+}
+
+long long gh_attn_head_bwd_workspace(int B, int L, int E) {
+  return 2LL * B * E + 3LL * B * L * E;
+}
+
+int gh_attn_head_bwd(const float* desc, const float* W_in, const float* W_out, const float* W_c, const float* qkv,
+                     const float* probs, const float* obar, const float* emb, const float* d_logits,
+                     const float* d_emb_ext, int B, int L, int E, int nc, float* d_desc, float* dW_in, float* db_in,
+                     float* dW_out, float* db_out, float* dW_c, float* db_c, float* workspace, void* stream) {
+  if (!desc || !W_in || !W_out || !W_c || !qkv || !probs || !obar || !emb || !d_logits || !workspace)
+    return GH_ERR_BAD_ARG;
+  if (B <= 0 || L <= 0 || E <= 0 || nc <= 0) return GH_ERR_BAD_ARG;
+  if (L > kMaxL) return GH_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* demb = workspace;                    // (B, E)
+  float* dobar = demb + (long long)B * E;     // (B, E)
+  float* dqkv = dobar + (long long)B * E;     // (B*L, 3E)
+  cudaError_t e;
+  // demb = d_logits W_c (+ d_emb_ext)
+  if (d_emb_ext) {
+    e = cudaMemcpyAsync(demb, d_emb_ext, (size_t)B * E * 4, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  e = launch_sgemm(d_logits, nc, 1, W_c, E, 1, nullptr, demb, E, B, E, nc, d_emb_ext ? 1 : 0, st);
+  if (e != cudaSuccess) return (int)e;
+  if (dW_c) {   // dW_c = d_logits^T emb   (nc, E)
+    e = launch_sgemm(d_logits, 1, nc, emb, E, 1, nullptr, dW_c, E, nc, E, B, 0, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  if (db_c) colsum_kernel<<<(nc + 31) / 32, dim3(32, 8), 0, st>>>(d_logits, nc, db_c, B, nc);
+  if (dW_out) {   // dW_out = demb^T Obar  (E, E)
+    e = launch_sgemm(demb, 1, E, obar, E, 1, nullptr, dW_out, E, E, E, B, 0, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  if (db_out) colsum_kernel<<<(E + 31) / 32, dim3(32, 8), 0, st>>>(demb, E, db_out, B, E);
+  // dObar = demb W_out             (B, E)
+  e = launch_sgemm(demb, E, 1, W_out, E, 1, nullptr, dobar, E, B, E, E, 0, st);
+  if (e != cudaSuccess) return (int)e;
+  attn_core_bwd_kernel<<<B, 128, 0, st>>>(qkv, probs, dobar, dqkv, L, E);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  if (dW_in) {   // dW_in = dQKV^T X       (3E, E)
+    e = launch_sgemm(dqkv, 1, 3LL * E, desc, E, 1, nullptr, dW_in, E, 3 * E, E, B * L, 0, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  if (db_in) colsum_kernel<<<(3 * E + 31) / 32, dim3(32, 8), 0, st>>>(dqkv, 3LL * E, db_in, B * L, 3 * E);
+  if (d_desc) {  // dX = dQKV W_in         (B*L, E)
+    e = launch_sgemm(dqkv, 3LL * E, 1, W_in, E, 1, nullptr, d_desc, E, B * L, E, 3 * E, 0, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -1,0 +1,418 @@
+"""Task-level functions around the Gram + attention model: same names, signatures and observable behaviour as the
+reference's functions/functions_RESNET50_Truncate_Gram_Attention.py (cited per function as file:line of that file),
+re-written for the B200 module. GUI / plotting imports are lazy, so importing this file needs only torch + numpy.
+
+Not replicated on purpose: the reference switches torch.autograd.set_detect_anomaly(True) on at import (:23).
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+from datetime import datetime
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.utils.data import Subset
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# checkpoints  (:30-120)
+# ---------------------------------------------------------------------------------------------------------------------
+def load_model(model, model_path, device):
+    """Initialise the encoder from a bare-encoder state_dict (:30-59): every checkpoint key `k` other than `fc.*` is
+    tried as `truncated_encoder.k`; keys that do not exist in the model are silently dropped; the merged dict is then
+    loaded strictly. Raises FileNotFoundError when the file is missing."""
+    if not os.path.isfile(model_path):
+        raise FileNotFoundError(f"No model found at {model_path}")
+    print(f"Loading pre-trained ResNet50 model from {model_path}")
+    checkpoint = torch.load(model_path, map_location=device)
+    merged = model.state_dict()
+    for key, value in checkpoint.items():
+        if key.startswith('fc.'):
+            continue
+        target = f"truncated_encoder.{key}"
+        if target in merged:
+            merged[target] = value
+    model.load_state_dict(merged, strict=True)
+    print("Model loaded successfully.")
+
+
+_SECTIONS = ('truncated_encoder', 'classifier', 'attention')
+
+
+def save_model_weights(model, save_path):
+    """Three-section checkpoint {'truncated_encoder', 'classifier', 'attention'} of sub-state-dicts (:63-70)."""
+    torch.save({name: getattr(model, name).state_dict() for name in _SECTIONS}, save_path)
+    print(f"Model weights saved to {save_path}")
+
+
+def load_model_weights(model, load_path):
+    """Loads a three-section checkpoint strictly, section by section, warning about absent sections; if that raises
+    KeyError/RuntimeError, re-reads the file as a flat dict with `<section>.` prefixes (:73-120). A missing file is
+    reported and ignored."""
+    if not os.path.isfile(load_path):
+        print(f"No weights file found at {load_path}. Proceeding without loading weights.")
+        return
+    state = torch.load(load_path, map_location=model.device)
+    try:
+        for name in _SECTIONS:
+            if name in state:
+                getattr(model, name).load_state_dict(state[name], strict=True)
+            else:
+                print(f"Warning: '{name}' not found in state_dict.")
+        print(f"Model weights loaded from {load_path} using direct method.")
+    except (KeyError, RuntimeError) as err:
+        print(f"Direct loading failed with error: {err}")
+        print("Attempting to load weights by processing keys...")
+        split = {name: {} for name in _SECTIONS}
+        for key, value in state.items():
+            for name in _SECTIONS:
+                if key.startswith(name):
+                    split[name][key.replace(f'{name}.', '')] = value
+                    break
+        for name in _SECTIONS:
+            getattr(model, name).load_state_dict(split[name], strict=True)
+        print(f"Model weights loaded from {load_path} by processing keys.")
+
+
+def set_parameter_requires_grad(model, freeze_encoder):
+    """freeze_encoder: only parameters whose name contains 'classifier' or 'attention' stay trainable (:226-236)."""
+    for name, param in model.named_parameters():
+        if not freeze_encoder:
+            param.requires_grad = True
+        elif "classifier" in name or "attention" in name:
+            param.requires_grad = True
+            print(f"Layer {name} is unfrozen.")
+        else:
+            param.requires_grad = False
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# training / evaluation loops  (:123-224)
+# ---------------------------------------------------------------------------------------------------------------------
+def _default_device():
+    return torch.device('cuda' if torch.cuda.is_available() else 'cpu')
+
+
+def train_model(model, train_loader, criterion, optimizer, num_epochs=25, writer=None, fold=0):
+    """SGD loop of the train script (:123-145): per batch zero_grad / forward / loss / backward / step, a loss print per
+    batch, the sample-weighted epoch loss printed and logged as Fold_{fold}/Train/Loss. Returns the model."""
+    device = _default_device()
+    model.to(device)
+    model.train()
+    n_batches = len(train_loader)
+    for epoch in range(num_epochs):
+        running = 0.0
+        for step, (inputs, labels) in enumerate(train_loader):
+            inputs = inputs.to(device, non_blocking=True)
+            labels = labels.to(device, non_blocking=True)
+            optimizer.zero_grad()
+            loss = criterion(model(inputs), labels)
+            loss.backward()
+            optimizer.step()
+            value = loss.item()
+            running += value * inputs.size(0)
+            print(f'Fold {fold}, Epoch [{epoch + 1}/{num_epochs}], Batch [{step + 1}/{n_batches}], Loss: {value:.4f}')
+        epoch_loss = running / len(train_loader.dataset)
+        print(f'Fold {fold}, Epoch [{epoch + 1}/{num_epochs}], Loss: {epoch_loss:.4f}')
+        if writer:
+            writer.add_scalar(f"Fold_{fold}/Train/Loss", epoch_loss, epoch)
+    return model
+
+
+def evaluate_model(model, val_loader, criterion, writer=None, fold=0):
+    """Validation pass (:148-176) -> (loss, accuracy, weighted precision, weighted recall)."""
+    from sklearn.metrics import precision_score, recall_score
+    device = _default_device()
+    model.to(device)
+    model.eval()
+    loss_sum = 0.0
+    correct = torch.zeros((), dtype=torch.long, device=device)
+    preds_all, labels_all = [], []
+    with torch.no_grad():
+        for inputs, labels in val_loader:
+            inputs = inputs.to(device, non_blocking=True)
+            labels = labels.to(device, non_blocking=True)
+            outputs = model(inputs)
+            loss_sum += criterion(outputs, labels).item() * inputs.size(0)
+            preds = outputs.argmax(dim=1)
+            correct += (preds == labels).sum()
+            preds_all.extend(preds.cpu().numpy())
+            labels_all.extend(labels.cpu().numpy())
+    n = len(val_loader.dataset)
+    total_loss = loss_sum / n
+    accuracy = correct.double() / n
+    precision = precision_score(labels_all, preds_all, average='weighted', zero_division=0)
+    recall = recall_score(labels_all, preds_all, average='weighted', zero_division=0)
+    print(f'Fold {fold}, Validation Loss: {total_loss:.4f}, Accuracy: {accuracy:.4f}, Precision: {precision:.4f}, '
+          f'Recall: {recall:.4f}')
+    if writer:
+        writer.add_scalar(f"Fold_{fold}/Validation/Loss", total_loss)
+        writer.add_scalar(f"Fold_{fold}/Validation/Accuracy", accuracy)
+        writer.add_scalar(f"Fold_{fold}/Validation/Precision", precision)
+        writer.add_scalar(f"Fold_{fold}/Validation/Recall", recall)
+    return total_loss, accuracy.item(), precision, recall
+
+
+def evaluate_model_test(model, data_loader, device):
+    """Test pass with the `_for_test` model (:178-224) -> (embeddings (N, g*g), preds, labels, probs (N, nc), paths).
+    Image paths are recovered from batch_idx * loader.batch_size, i.e. the loader must not shuffle (as in the reference).
+    """
+    model.eval()
+    emb_all, prob_all, pred_all, label_all, paths = [], [], [], [], []
+    dataset = data_loader.dataset
+    with torch.no_grad():
+        for batch_idx, (inputs, labels) in enumerate(data_loader):
+            inputs = inputs.to(device, non_blocking=True)
+            embeddings, outputs = model(inputs)
+            probs = F.softmax(outputs, dim=1)
+            preds = outputs.argmax(dim=1)
+            emb_all.append(embeddings.cpu().numpy())
+            prob_all.append(probs.cpu().numpy())
+            pred_all.extend(preds.cpu().numpy())
+            label_all.extend(labels.cpu().numpy())
+            first = batch_idx * data_loader.batch_size
+            for j in range(inputs.size(0)):
+                if isinstance(dataset, Subset):
+                    paths.append(dataset.dataset.samples[dataset.indices[first + j]][0])
+                else:
+                    paths.append(dataset.samples[first + j][0])
+    return (np.concatenate(emb_all, axis=0), np.array(pred_all), np.array(label_all),
+            np.concatenate(prob_all, axis=0), paths)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# style transfer  (:241-314)
+# ---------------------------------------------------------------------------------------------------------------------
+def denormalize(tensor, mean, std):
+    """In-place per-channel x*std + mean (:241-246)."""
+    mean = mean.to(tensor.device)
+    std = std.to(tensor.device)
+    for channel, m, s in zip(tensor, mean, std):
+        channel.mul_(s).add_(m)
+    return tensor
+
+
+def _save_side_by_side(path, image):
+    try:
+        import matplotlib.pyplot as plt
+        plt.imsave(path, image)
+    except Exception:
+        from PIL import Image
+        Image.fromarray((np.clip(image, 0, 1) * 255).astype(np.uint8)).save(path)
+
+
+def style_transfer(model, data_loader, device, save_dir, layers=None, threshold=1e-4, num_iterations=500,
+                   learning_rate=0.01):
+    """For every image: optimise a noise image with Adam so that the dense Gram of the first `layers` encoder children
+    matches the image's (MSE), stop below `threshold`, save original|result under save_dir/style_transfer_<date>/<label>
+    (:247-314). Both Gram evaluations and the gradient through them go through model.gram_matrix(), i.e. the dense
+    tcgen05 forward/backward kernels."""
+    model.eval()
+    out_root = os.path.join(save_dir, f'style_transfer_{datetime.now().strftime("%Y-%m-%d")}')
+    os.makedirs(out_root, exist_ok=True)
+    mse = nn.MSELoss()
+    mean = torch.tensor([0.485, 0.456, 0.406], device=device)
+    std = torch.tensor([0.229, 0.224, 0.225], device=device)
+    for inputs, labels in data_loader:
+        inputs, labels = inputs.to(device), labels.to(device)
+        for i, image in enumerate(inputs):
+            image = image.unsqueeze(0)
+            encoder = nn.Sequential(*list(model.truncated_encoder.children())[:layers]).to(device)
+            with torch.no_grad():
+                target = model.gram_matrix(encoder(image))
+            class_dir = os.path.join(out_root, str(labels[i].item()))
+            os.makedirs(class_dir, exist_ok=True)
+            noise = torch.randn((1, 3, 224, 224), device=device, requires_grad=True)
+            optimizer = torch.optim.Adam([noise], lr=learning_rate)
+            for iteration in range(num_iterations):
+                optimizer.zero_grad()
+                loss = mse(model.gram_matrix(encoder(noise)), target)
+                loss.backward()
+                optimizer.step()
+                if loss.item() < threshold:
+                    print(f"Seuil atteint pour l'image {i}, itération {iteration}")
+                    break
+            result = denormalize(noise.detach().cpu().squeeze(), mean, std).clamp_(0, 1).numpy().transpose(1, 2, 0)
+            original = denormalize(image.detach().cpu().squeeze(), mean, std).clamp_(0, 1).numpy().transpose(1, 2, 0)
+            save_path = os.path.join(class_dir, f'style_transfer_{i}.png')
+            _save_side_by_side(save_path, np.hstack((original, result)))
+            print(f"Style transféré pour l'image {i}, sauvegardée à {save_path}")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# config  (:329-337)
+# ---------------------------------------------------------------------------------------------------------------------
+def load_hyperparameters(hyperparams_path):
+    if not os.path.isfile(hyperparams_path):
+        print(f"No hyperparameters file found at {hyperparams_path}. Proceeding with default hyperparameters.")
+        return None
+    with open(hyperparams_path, 'r') as f:
+        hyperparams = json.load(f)
+    print(f"Hyperparameters loaded from {hyperparams_path}")
+    return hyperparams
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# t-SNE views (:343-474): CPU/GUI post-processing of the embeddings, outside the accelerated path; kept so that the
+# reference's test script imports resolve and the non-interactive plot works when matplotlib is installed.
+# ---------------------------------------------------------------------------------------------------------------------
+def _label_colors(labels, colors, plt):
+    unique = np.unique(labels)
+    if colors and len(colors) >= len(unique):
+        return unique, {label: colors[i] for i, label in enumerate(unique)}
+    palette = plt.cm.get_cmap("tab20", len(unique))
+    return unique, {label: palette(label) for label in unique}
+
+
+def perform_tsne(embeddings, labels, save_path, colors=None):
+    from sklearn.manifold import TSNE
+    import matplotlib.pyplot as plt
+    points = TSNE(n_components=2, random_state=0).fit_transform(embeddings)
+    plt.figure(figsize=(10, 10))
+    unique, cmap = _label_colors(labels, colors, plt)
+    for label in unique:
+        sel = labels == label
+        plt.scatter(points[sel, 0], points[sel, 1], label=f'Class {label}', color=cmap[int(label)])
+    plt.legend()
+    plt.title('t-SNE of Embeddings')
+    plt.savefig(save_path)
+    plt.show()
+    print(f"t-SNE visualization saved to {save_path}")
+
+
+def create_onpick_function(dataset, img_paths, img_label, label_text, classes, labels):
+    def onpick(event):
+        from PIL import Image, ImageTk
+        idx = event.ind[0]
+        print(f"Selected img_path: {img_paths[idx]}")
+        picture = ImageTk.PhotoImage(Image.open(img_paths[idx]).resize((400, 400), Image.LANCZOS))
+        img_label.configure(image=picture)
+        img_label.image = picture
+        label_text.set(f"Label: {classes[int(labels[idx])]}")
+    return onpick
+
+
+def plot_tsne_interactive(embeddings, labels, classes, img_paths, dataset, colors=None):
+    """Tk window with a pickable t-SNE scatter and a polygon selector (:377-474). Needs tkinter + matplotlib."""
+    from sklearn.manifold import TSNE
+    import tkinter as tk
+    import matplotlib.pyplot as plt
+    from matplotlib.backends.backend_tkagg import FigureCanvasTkAgg
+    from matplotlib.widgets import PolygonSelector
+    from matplotlib.path import Path
+
+    points = TSNE(n_components=2, random_state=42).fit_transform(embeddings)
+    root = tk.Tk()
+    root.title("Interactive t-SNE with Images")
+    fig, ax = plt.subplots(figsize=(10, 10))
+    unique, cmap = _label_colors(labels, colors, plt)
+    scatter = ax.scatter(points[:, 0], points[:, 1], c=[cmap[int(v)] for v in labels], picker=True)
+    ax.legend(handles=scatter.legend_elements()[0], labels=[classes[int(v)] for v in unique])
+    img_label = tk.Label(root)
+    img_label.grid(row=0, column=1, sticky='nsew')
+    label_text = tk.StringVar()
+    tk.Label(root, textvariable=label_text).grid(row=1, column=1, sticky='nsew')
+    fig.canvas.mpl_connect('pick_event', create_onpick_function(dataset, img_paths, img_label, label_text, classes, labels))
+    canvas = FigureCanvasTkAgg(fig, master=root)
+    canvas.draw()
+    canvas.get_tk_widget().grid(row=0, column=0, rowspan=2, sticky='nsew')
+
+    state = {"polygon": [], "selector": None, "cleared": True}
+
+    def on_select(vertices):
+        state["polygon"] = list(vertices)
+        print("Polygon vertices:", vertices)
+
+    def on_button(event):
+        if event.button == 3 and (state["selector"] is None or state["cleared"]):
+            state["selector"] = PolygonSelector(ax, onselect=on_select, useblit=True)
+            state["cleared"] = False
+            print("Polygon selector enabled.")
+
+    def analyze():
+        if len(state["polygon"]) < 3:
+            print("Polygon not closed. Select at least 3 points.")
+            return
+        region = Path(state["polygon"])
+        inside = sum(1 for x, y in points if region.contains_point((x, y)))
+        print(f"Points inside polygon: {inside}")
+
+    def clear():
+        state["polygon"] = []
+        if state["selector"] is not None:
+            state["selector"].disconnect_events()
+            state["selector"].set_visible(False)
+            state["selector"] = None
+        while ax.patches:
+            ax.patches.pop().remove()
+        fig.canvas.draw()
+        state["cleared"] = True
+
+    fig.canvas.mpl_connect('button_press_event', on_button)
+    tk.Button(root, text="Close Polygon", command=analyze).grid(row=4, column=0, sticky='ew')
+    tk.Button(root, text="Clear Polygon", command=clear).grid(row=4, column=1, sticky='ew')
+    root.mainloop()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# camera streaming  (:477-536)
+# ---------------------------------------------------------------------------------------------------------------------
+def run_camera(model, transform, class_names, save_video, save_dir, prob_threshold, measure_time, capture=None,
+               display=True, max_frames=None):
+    """Per frame: BGR->RGB -> PIL -> transform -> model -> softmax -> label overlay; optional video file and
+    times_camera.json (:477-536). `capture`, `display`, `max_frames` are additions (defaults reproduce the reference:
+    cv2.VideoCapture(0), cv2.imshow, run until 'q'): any object with read()/isOpened()/release() can stand in for the
+    camera, which is how the streaming benchmark feeds synthetic 1080p frames."""
+    import cv2
+    from PIL import Image
+    model.eval()
+    cap = capture if capture is not None else cv2.VideoCapture(0)
+    if not cap.isOpened():
+        print("Error: Unable to open the camera")
+        return
+    out = None
+    if save_video:
+        os.makedirs(save_dir, exist_ok=True)
+        out = cv2.VideoWriter(os.path.join(save_dir, "camera_output.avi"), cv2.VideoWriter_fourcc(*'XVID'), 20.0,
+                              (640, 480))
+    times = []
+    frames = 0
+    with torch.no_grad():
+        while max_frames is None or frames < max_frames:
+            ok, frame = cap.read()
+            if not ok:
+                print("Error: Unable to read the image from the camera")
+                break
+            start = time.time()
+            rgb = cv2.cvtColor(frame, cv2.COLOR_BGR2RGB)
+            batch = transform(Image.fromarray(rgb)).unsqueeze(0).to(model.device)
+            _, outputs = model(batch)
+            probabilities = F.softmax(outputs, dim=1).cpu().numpy()[0]   # the .cpu() is the only sync, as upstream
+            best = int(np.argmax(probabilities))
+            prob = probabilities[best]
+            name = class_names[best] if prob >= prob_threshold else "Unknown"
+            times.append(time.time() - start)
+            frames += 1
+            cv2.putText(frame, f"Pred: {name}, Prob: {prob:.4f}", (10, 25), cv2.FONT_HERSHEY_SIMPLEX, 0.7, (0, 255, 0), 2)
+            if display:
+                cv2.imshow('Camera', frame)
+            if out is not None:
+                out.write(frame)
+            if display and (cv2.waitKey(1) & 0xFF == ord('q')):
+                break
+    if measure_time:
+        os.makedirs(save_dir, exist_ok=True)
+        with open(os.path.join(save_dir, "times_camera.json"), "w") as f:
+            json.dump(times, f, indent=4)
+        print(f"Average processing time per image: {np.mean(times)} seconds")
+        print(f"Total processing time: {np.sum(times)} seconds")
+    cap.release()
+    if out is not None:
+        out.release()
+    if display:
+        cv2.destroyAllWindows()
+    return times

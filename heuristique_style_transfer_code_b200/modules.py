@@ -1,0 +1,84 @@
+"""Drop-in nn.Modules for the reference's Gram + attention classifier.
+
+Mirrors Models/Models_RESNET50_TRUNCATE_GRAM_with_Attention.py (reference tree): class names, constructor signature
+(:14 / :66), public attributes (device, truncated_encoder, num_classes, gram_matrix_size, classifier, attention),
+gram_matrix() (:26-30), forward() return conventions (:61 logits | :113-114 (embeddings, logits)), the zero-stage early
+return (:48-49) and therefore the state_dict keys (truncated_encoder.*, classifier.{weight,bias},
+attention.{in_proj_weight,in_proj_bias,out_proj.weight,out_proj.bias}). Submodules are created in the reference's order
+(encoder, classifier, attention) so a seeded construction consumes the RNG identically.
+
+What differs is how forward() computes: the backbone stays on cuDNN (as the task prescribes), everything after it --
+Gram, pooling, token layout, attention, mean, classifier and their backward -- runs in libgramhead.so's sm_100a
+kernels (ops.py). nn.MultiheadAttention / nn.Linear are kept purely as parameter containers. The module does not turn
+on torch.autograd.set_detect_anomaly (the reference does so at import, :9).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+class GramAttentionHead:
+    """Functional core shared by both classes: stage activations -> (embeddings, logits)."""
+
+    @staticmethod
+    def apply(stages, gram_matrix_size: int, attention: nn.MultiheadAttention, classifier: nn.Linear):
+        desc = ops.style_descriptor(stages, gram_matrix_size)
+        return ops.attention_head(desc, attention.in_proj_weight, attention.in_proj_bias, attention.out_proj.weight,
+                                  attention.out_proj.bias, classifier.weight, classifier.bias)
+
+
+class _TruncatedGramAttentionBase(nn.Module):
+    def __init__(self, base_encoder, truncate_after_layer, num_classes, gram_matrix_size, device='cpu'):
+        super().__init__()
+        self.device = device
+        self.truncated_encoder = nn.Sequential(*list(base_encoder.children())[:truncate_after_layer]).to(self.device)
+        self.num_classes = num_classes
+        self.gram_matrix_size = gram_matrix_size
+        self.classifier = nn.Linear(self.gram_matrix_size ** 2, self.num_classes).to(self.device)
+        self.attention = nn.MultiheadAttention(embed_dim=self.gram_matrix_size ** 2, num_heads=1).to(self.device)
+
+    def gram_matrix(self, activations):
+        """(b, ch, h, w) -> (b, ch, ch): F F^T / (h*w), differentiable (dense tcgen05 Gram kernels)."""
+        return ops.gram_matrix(activations)
+
+    def _stage_activations(self, x):
+        x = x.to(self.device)
+        enc = self.truncated_encoder
+        # conv1, bn1, relu, maxpool -- an encoder truncated below 4 children raises IndexError, as the reference does
+        x = enc[0](x)
+        x = enc[1](x)
+        x = enc[2](x)
+        x = enc[3](x)
+        stages = []
+        for block in enc[4:]:
+            x = block(x)
+            stages.append(x)
+        return x, stages
+
+    def _head(self, x):
+        x, stages = self._stage_activations(x)
+        if not stages:
+            return None, torch.zeros((x.size(0), self.num_classes), requires_grad=True).to(self.device)
+        return GramAttentionHead.apply(stages, self.gram_matrix_size, self.attention, self.classifier)
+
+
+class TruncatedResNet50(_TruncatedGramAttentionBase):
+    """Training variant: forward(x) -> logits (B, num_classes)."""
+
+    def forward(self, x):
+        _, logits = self._head(x)
+        return logits
+
+
+class TruncatedResNet50_for_test(_TruncatedGramAttentionBase):
+    """Evaluation variant: forward(x) -> (embeddings (B, g*g), logits (B, num_classes)).
+    With no Gram stages it returns the zero logits alone, exactly like the reference (:100-101)."""
+
+    def forward(self, x):
+        emb, logits = self._head(x)
+        if emb is None:
+            return logits
+        return emb, logits

@@ -1,0 +1,240 @@
+"""torch-facing wrappers (autograd.Function) over the C ABI in include/gramhead.h.
+
+PyTorch is used for device memory, streams and autograd bookkeeping only; every FLOP of the head runs in
+libgramhead.so. All functions require CUDA tensors and raise otherwise: there is no CPU / eager fallback.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import GH_DTYPE_BF16, GH_DTYPE_F32, GramHeadError, check
+
+# Launch knobs (tests and bench sweep them; 0 = library default)
+KSPLIT = 0
+MAX_CTAS = 0
+
+
+def _stream_ptr(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise GramHeadError(f"gramhead: {what} must be a CUDA tensor (got {t.device}); the head has no CPU path")
+
+
+def _feature_view(x: torch.Tensor) -> Tuple[torch.Tensor, int, int, int, int, int, int]:
+    """(B, C, H, W) or (B, C, HW) activation -> tensor kept alive, dtype code, img/row strides (elements), B, C, HW."""
+    _require_cuda(x, "features")
+    if x.dim() == 4:
+        b, c, h, w = x.shape
+        hw = h * w
+        # NCHW-contiguous spatial dims are required (the reference does .view(b, ch, h*w)); batch/channel may stride
+        if not (x.stride(3) == 1 and x.stride(2) == w):
+            x = x.contiguous()
+    elif x.dim() == 3:
+        b, c, hw = x.shape
+        if x.stride(2) != 1:
+            x = x.contiguous()
+    else:
+        raise GramHeadError(f"gramhead: features must be (B,C,H,W) or (B,C,HW), got {tuple(x.shape)}")
+    if x.dtype == torch.float32:
+        code = GH_DTYPE_F32
+    elif x.dtype == torch.bfloat16:
+        code = GH_DTYPE_BF16
+    else:
+        raise GramHeadError(f"gramhead: features must be float32 or bfloat16, got {x.dtype}")
+    return x, code, x.stride(0), x.stride(1), b, c, hw
+
+
+def pooled_supported(c: int, g: int) -> bool:
+    """True when the fused Gram+pool kernels apply (bins are disjoint k x k blocks with k a power of two <= 128)."""
+    if g <= 0 or c % g:
+        return False
+    k = c // g
+    return k <= 128 and (k & (k - 1)) == 0
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# raw launches
+# ----------------------------------------------------------------------------------------------------------------------
+def gram_pool_fwd_(x: torch.Tensor, g: int, desc: torch.Tensor, l: int) -> None:
+    """desc[:, l, :] = vec(pool_g(F F^T / HW)) for stage activation x. desc: (B, L, g*g) fp32 contiguous."""
+    x, code, s_img, s_row, b, c, hw = _feature_view(x)
+    assert desc.is_contiguous() and desc.dtype == torch.float32 and desc.shape[0] == b and desc.shape[2] == g * g
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().gh_gram_pool_fwd(x.data_ptr(), code, s_img, s_row, b, c, hw, g, desc.data_ptr(), l,
+                                         desc.shape[1], KSPLIT, MAX_CTAS, _stream_ptr(x))
+    check(rc, "gh_gram_pool_fwd")
+
+
+def gram_dense_fwd(x: torch.Tensor) -> torch.Tensor:
+    x, code, s_img, s_row, b, c, hw = _feature_view(x)
+    out = torch.empty((b, c, c), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().gh_gram_dense_fwd(x.data_ptr(), code, s_img, s_row, b, c, hw, out.data_ptr(), KSPLIT, MAX_CTAS,
+                                          _stream_ptr(x))
+    check(rc, "gh_gram_dense_fwd")
+    return out
+
+
+def gram_pool_bwd(x: torch.Tensor, g: int, d_desc: torch.Tensor, l: int) -> torch.Tensor:
+    x, code, s_img, s_row, b, c, hw = _feature_view(x)
+    d_desc = d_desc.contiguous()
+    df = torch.empty((b, c, hw), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().gh_gram_pool_bwd(x.data_ptr(), code, s_img, s_row, b, c, hw, g, d_desc.data_ptr(), l,
+                                         d_desc.shape[1], df.data_ptr(), c * hw, hw, MAX_CTAS, _stream_ptr(x))
+    check(rc, "gh_gram_pool_bwd")
+    return df
+
+
+def gram_dense_bwd(x: torch.Tensor, d_gram: torch.Tensor) -> torch.Tensor:
+    x, code, s_img, s_row, b, c, hw = _feature_view(x)
+    d_gram = d_gram.contiguous().float()
+    df = torch.empty((b, c, hw), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().gh_gram_dense_bwd(x.data_ptr(), code, s_img, s_row, b, c, hw, d_gram.data_ptr(), df.data_ptr(),
+                                          c * hw, hw, MAX_CTAS, _stream_ptr(x))
+    check(rc, "gh_gram_dense_bwd")
+    return df
+
+
+def adaptive_pool_fwd_(gram: torch.Tensor, g: int, desc: torch.Tensor, l: int) -> None:
+    b, c, _ = gram.shape
+    with torch.cuda.device(gram.device):
+        rc = _lib.lib().gh_adaptive_pool_fwd(gram.data_ptr(), b, c, g, desc.data_ptr(), l, desc.shape[1],
+                                             _stream_ptr(gram))
+    check(rc, "gh_adaptive_pool_fwd")
+
+
+def adaptive_pool_bwd(d_desc: torch.Tensor, l: int, c: int, g: int) -> torch.Tensor:
+    d_desc = d_desc.contiguous()
+    b = d_desc.shape[0]
+    dg = torch.empty((b, c, c), device=d_desc.device, dtype=torch.float32)
+    with torch.cuda.device(d_desc.device):
+        rc = _lib.lib().gh_adaptive_pool_bwd(d_desc.data_ptr(), l, d_desc.shape[1], b, c, g, dg.data_ptr(),
+                                             _stream_ptr(d_desc))
+    check(rc, "gh_adaptive_pool_bwd")
+    return dg
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# autograd
+# ----------------------------------------------------------------------------------------------------------------------
+class _GramDense(torch.autograd.Function):
+    """model.gram_matrix(x): (B, C, H, W) -> (B, C, C)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return gram_dense_fwd(x)
+
+    @staticmethod
+    def backward(ctx, d_gram):
+        (x,) = ctx.saved_tensors
+        df = gram_dense_bwd(x, d_gram)
+        return df.view(x.shape).to(x.dtype)
+
+
+def gram_matrix(x: torch.Tensor) -> torch.Tensor:
+    return _GramDense.apply(x)
+
+
+class _StyleDescriptor(torch.autograd.Function):
+    """L stage activations -> (B, L, g*g) pooled-Gram descriptors (the attention's input, batch-major)."""
+
+    @staticmethod
+    def forward(ctx, g, *stages):
+        b = stages[0].shape[0]
+        L = len(stages)
+        desc = torch.empty((b, L, g * g), device=stages[0].device, dtype=torch.float32)
+        for l, x in enumerate(stages):
+            if pooled_supported(x.shape[1], g):
+                gram_pool_fwd_(x, g, desc, l)
+            else:   # torch's general (overlapping) bins: dense Gram, then the bin-rule pooling kernel
+                adaptive_pool_fwd_(gram_dense_fwd(x), g, desc, l)
+        ctx.g = g
+        ctx.save_for_backward(*stages)
+        return desc
+
+    @staticmethod
+    def backward(ctx, d_desc):
+        g = ctx.g
+        d_desc = d_desc.contiguous().float()
+        grads: List[object] = [None]
+        for l, x in enumerate(ctx.saved_tensors):
+            if not ctx.needs_input_grad[l + 1]:
+                grads.append(None)
+                continue
+            c = x.shape[1]
+            if pooled_supported(c, g) and g <= 64 and c % 16 == 0:
+                df = gram_pool_bwd(x, g, d_desc, l)
+            else:
+                df = gram_dense_bwd(x, adaptive_pool_bwd(d_desc, l, c, g))
+            grads.append(df.view(x.shape).to(x.dtype))
+        return tuple(grads)
+
+
+def style_descriptor(stages: Sequence[torch.Tensor], g: int) -> torch.Tensor:
+    return _StyleDescriptor.apply(g, *stages)
+
+
+class _AttnHead(torch.autograd.Function):
+    """(B, L, E) descriptors + the six head parameters -> (embeddings (B, E), logits (B, nc))."""
+
+    @staticmethod
+    def forward(ctx, desc, w_in, b_in, w_out, b_out, w_c, b_c):
+        _require_cuda(desc, "descriptors")
+        desc = desc.contiguous().float()
+        ps = [t.contiguous().float() for t in (w_in, b_in, w_out, b_out, w_c, b_c)]
+        b, L, e = desc.shape
+        nc = ps[4].shape[0]
+        dev = desc.device
+        qkv = torch.empty((b * L, 3 * e), device=dev, dtype=torch.float32)
+        probs = torch.empty((b, L, L), device=dev, dtype=torch.float32)
+        obar = torch.empty((b, e), device=dev, dtype=torch.float32)
+        emb = torch.empty((b, e), device=dev, dtype=torch.float32)
+        logits = torch.empty((b, nc), device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().gh_attn_head_fwd(desc.data_ptr(), *[p.data_ptr() for p in ps], b, L, e, nc, qkv.data_ptr(),
+                                             probs.data_ptr(), obar.data_ptr(), emb.data_ptr(), logits.data_ptr(),
+                                             _stream_ptr(desc))
+        check(rc, "gh_attn_head_fwd")
+        ctx.save_for_backward(desc, ps[0], ps[2], ps[4], qkv, probs, obar, emb)
+        ctx.dims = (b, L, e, nc)
+        return emb, logits
+
+    @staticmethod
+    def backward(ctx, d_emb, d_logits):
+        desc, w_in, w_out, w_c, qkv, probs, obar, emb = ctx.saved_tensors
+        b, L, e, nc = ctx.dims
+        dev = desc.device
+        need = ctx.needs_input_grad
+        d_logits = (torch.zeros((b, nc), device=dev) if d_logits is None else d_logits).contiguous().float()
+        d_emb = None if d_emb is None else d_emb.contiguous().float()
+
+        def buf(flag, shape):
+            return torch.empty(shape, device=dev, dtype=torch.float32) if flag else None
+
+        d_desc = buf(need[0], (b, L, e))
+        gw_in, gb_in = buf(need[1], (3 * e, e)), buf(need[2], (3 * e,))
+        gw_out, gb_out = buf(need[3], (e, e)), buf(need[4], (e,))
+        gw_c, gb_c = buf(need[5], (nc, e)), buf(need[6], (nc,))
+        lib = _lib.lib()
+        ws = torch.empty((lib.gh_attn_head_bwd_workspace(b, L, e),), device=dev, dtype=torch.float32)
+        ptr = lambda t: 0 if t is None else t.data_ptr()
+        with torch.cuda.device(dev):
+            rc = lib.gh_attn_head_bwd(desc.data_ptr(), w_in.data_ptr(), w_out.data_ptr(), w_c.data_ptr(), qkv.data_ptr(),
+                                      probs.data_ptr(), obar.data_ptr(), emb.data_ptr(), d_logits.data_ptr(), ptr(d_emb),
+                                      b, L, e, nc, ptr(d_desc), ptr(gw_in), ptr(gb_in), ptr(gw_out), ptr(gb_out),
+                                      ptr(gw_c), ptr(gb_c), ws.data_ptr(), _stream_ptr(desc))
+        check(rc, "gh_attn_head_bwd")
+        return d_desc, gw_in, gb_in, gw_out, gb_out, gw_c, gb_c
+
+
+def attention_head(desc, w_in, b_in, w_out, b_out, w_c, b_c):
+    return _AttnHead.apply(desc, w_in, b_in, w_out, b_out, w_c, b_c)

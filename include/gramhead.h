@@ -1,0 +1,104 @@
+/* gramhead.h - C ABI of libgramhead.so, the sm_100a implementation of the Gram + attention style-feature head of
+ * Hamedkiri/heuristique_style_transfer_code (model "TruncatedResNet50 + Gram + Attention").
+ *
+ * Every entry point replaces a piece of the reference's Python hot path; the reference interface each one stands
+ * in for is cited as file:line relative to the reference tree. The reference has no FFI of its own (it is pure
+ * PyTorch), so the binding a maintainer adds is the ctypes stub shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers on the current CUDA device unless stated otherwise;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); calls only enqueue work, they never
+ *     synchronise the host and never allocate device memory;
+ *   - tensors are dense row-major unless a stride argument says otherwise; fp32 buffers must be 4-byte aligned
+ *     (16-byte alignment enables the vector load path);
+ *   - return value: 0 = ok; > 0 = a cudaError_t from the launch; < 0 = GH_ERR_* below.
+ */
+#ifndef GRAMHEAD_H_
+#define GRAMHEAD_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GH_ERR_BAD_ARG (-1)       /* null pointer / non-positive size */
+#define GH_ERR_UNSUPPORTED (-2)   /* shape outside what this entry point implements; see its comment */
+
+#define GH_DTYPE_F32 0
+#define GH_DTYPE_BF16 1
+
+/* Library version (major*10000 + minor*100 + patch). */
+int gh_version(void);
+
+/* Number of SMs the launchers size their persistent grids by (cudaDevAttrMultiProcessorCount of the current device). */
+int gh_sm_count(void);
+
+/* Copies the device-side error record {code, blockIdx.x, threadIdx.x, site} to host memory `out4` and clears it.
+ * code 1 = an mbarrier wait inside a kernel ran out of time (the kernel traps instead of hanging). Synchronises. */
+int gh_last_device_error(unsigned int* out4);
+
+/* Pooled Gram, forward.  Replaces, for one encoder stage l of L,
+ *   gram_matrix():            Models/Models_RESNET50_TRUNCATE_GRAM_with_Attention.py:26-30 (bmm + div(h*w))
+ *   adaptive_avg_pool2d:      :51-52
+ *   stack/flatten (layout):   :54-55
+ * F: (B, C, HW) features, element (b,c,x) at F[b*img_stride + c*row_stride + x], dtype f_dtype.
+ * desc: (B, L, g*g) fp32; this call overwrites desc[:, l, :] with vec_rowmajor(pool_g(F F^T / HW)).
+ * Requires C % g == 0 and k = C/g a power of two <= 128 (returns GH_ERR_UNSUPPORTED otherwise: use
+ * gh_gram_dense_fwd + gh_adaptive_pool_fwd, which implement torch's general bin rule).
+ * ksplit: number of K (=HW) partitions per tile whose partial sums meet in fp32 atomics; 0 = choose for load balance,
+ * 1 = deterministic summation order. max_ctas: 0 = one persistent CTA per SM. */
+int gh_gram_pool_fwd(const void* F, int f_dtype, long long img_stride, long long row_stride, int B, int C, int HW,
+                     int g, float* desc, int l, int L, int ksplit, int max_ctas, void* stream);
+
+/* Dense Gram, forward: G[b] = F[b] F[b]^T / HW, (B, C, C) fp32, both triangles written.
+ * Replaces gram_matrix() used on its own (:26-30; style-transfer mode,
+ * functions/functions_RESNET50_Truncate_Gram_Attention.py:273-275,290-291). */
+int gh_gram_dense_fwd(const void* F, int f_dtype, long long img_stride, long long row_stride, int B, int C, int HW,
+                      float* G, int ksplit, int max_ctas, void* stream);
+
+/* torch.nn.functional.adaptive_avg_pool2d(G, (g, g)) on (B, C, C) with torch's bin rule
+ * [floor(i*C/g), ceil((i+1)*C/g)), written to desc[:, l, :] of a (B, L, g*g) buffer.  (:51-55) */
+int gh_adaptive_pool_fwd(const float* G, int B, int C, int g, float* desc, int l, int L, void* stream);
+/* Its backward: dG (B, C, C) from d_desc[:, l, :]. */
+int gh_adaptive_pool_bwd(const float* d_desc, int l, int L, int B, int C, int g, float* dG, void* stream);
+
+/* Pooled Gram, backward (autograd of the three reference lines above):
+ *   dF[b] = (dG + dG^T) F[b] / HW,  dG[c][d] = d_desc[b, l, (c/k)*g + d/k] / k^2.
+ * dF: fp32, element (b,c,x) at dF[b*df_img_stride + c*df_row_stride + x]; overwritten.
+ * Requires C % g == 0, k a power of two, g <= 64, C % 16 == 0. */
+int gh_gram_pool_bwd(const void* F, int f_dtype, long long img_stride, long long row_stride, int B, int C, int HW,
+                     int g, const float* d_desc, int l, int L, float* dF, long long df_img_stride,
+                     long long df_row_stride, int max_ctas, void* stream);
+
+/* Dense Gram, backward: dF[b] = (dG[b] + dG[b]^T) F[b] / HW with dG (B, C, C) fp32. Requires C % 16 == 0. */
+int gh_gram_dense_bwd(const void* F, int f_dtype, long long img_stride, long long row_stride, int B, int C, int HW,
+                      const float* dG, float* dF, long long df_img_stride, long long df_row_stride, int max_ctas,
+                      void* stream);
+
+/* Attention over the L stage descriptors + mean over stages + classifier, forward.  Replaces
+ *   permute + self.attention(X, X, X) (nn.MultiheadAttention, 1 head): :56-58
+ *   .mean(dim=0):                                                     :59
+ *   self.classifier(...):                                             :61 / :113-114
+ * desc (B, L, E) fp32 with E = g*g; W_in (3E, E), b_in (3E), W_out (E, E), b_out (E), W_c (nc, E), b_c (nc):
+ * the tensors of attention.in_proj_weight/.in_proj_bias/.out_proj.weight/.out_proj.bias and classifier.weight/.bias.
+ * Outputs: emb (B, E) (the `embeddings` of TruncatedResNet50_for_test), logits (B, nc); saved for backward:
+ * qkv (B*L, 3E), probs (B, L, L), obar (B, E). L <= 8. */
+int gh_attn_head_fwd(const float* desc, const float* W_in, const float* b_in, const float* W_out, const float* b_out,
+                     const float* W_c, const float* b_c, int B, int L, int E, int nc, float* qkv, float* probs,
+                     float* obar, float* emb, float* logits, void* stream);
+
+/* Number of fp32 elements gh_attn_head_bwd needs in `workspace`. */
+long long gh_attn_head_bwd_workspace(int B, int L, int E);
+
+/* Backward of gh_attn_head_fwd (what loss.backward() runs for those lines; functions/...Attention.py:135).
+ * Inputs: the forward's inputs and saved tensors, d_logits (B, nc), d_emb_ext (B, E) or NULL (gradient arriving
+ * directly at the embeddings output). Outputs (each may be NULL to skip it; all are overwritten, not accumulated):
+ * d_desc (B, L, E), dW_in, db_in, dW_out, db_out, dW_c, db_c. */
+int gh_attn_head_bwd(const float* desc, const float* W_in, const float* W_out, const float* W_c, const float* qkv,
+                     const float* probs, const float* obar, const float* emb, const float* d_logits,
+                     const float* d_emb_ext, int B, int L, int E, int nc, float* d_desc, float* dW_in, float* db_in,
+                     float* dW_out, float* db_out, float* dW_c, float* db_c, float* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAMHEAD_H_ */

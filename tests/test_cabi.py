@@ -1,0 +1,56 @@
+"""The C-ABI shared library loads on a CPU-only machine and exports exactly what include/gramhead.h declares.
+No compute call is made here (argument validation returns before any CUDA API is touched)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+from heuristique_style_transfer_code_b200 import _lib
+from heuristique_style_transfer_code_b200.build import build_library
+
+
+@pytest.fixture(scope="module")
+def library():
+    build_library()
+    return _lib.lib()
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "gramhead.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gh_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    assert declared_symbols() == sorted(_lib.EXPORTED_SYMBOLS)
+
+
+def test_every_declared_symbol_is_exported(library):
+    for name in declared_symbols():
+        assert hasattr(library, name), name
+
+
+def test_version(library):
+    assert library.gh_version() >= 100
+
+
+def test_argument_validation_without_gpu(library):
+    assert library.gh_gram_pool_fwd(None, 0, 0, 0, 1, 256, 64, 32, None, 0, 1, 0, 0, None) == _lib.GH_ERR_BAD_ARG
+    assert library.gh_gram_dense_fwd(None, 0, 0, 0, 1, 256, 64, None, 0, 0, None) == _lib.GH_ERR_BAD_ARG
+    assert library.gh_attn_head_fwd(*([None] * 7), 1, 3, 64, 4, *([None] * 5), None) == _lib.GH_ERR_BAD_ARG
+    assert library.gh_gram_pool_bwd(None, 0, 0, 0, 1, 256, 64, 32, None, 0, 1, None, 0, 0, 0, None) == _lib.GH_ERR_BAD_ARG
+    dummy = ctypes.c_void_p(16)
+    # non-power-of-two pooling factor and oversize g are refused before any launch
+    assert library.gh_gram_pool_fwd(dummy, 0, 0, 0, 1, 96, 64, 32, dummy, 0, 1, 0, 0, None) == _lib.GH_ERR_UNSUPPORTED
+    assert library.gh_gram_pool_fwd(dummy, 0, 0, 0, 1, 100, 64, 32, dummy, 0, 1, 0, 0, None) == _lib.GH_ERR_UNSUPPORTED
+    assert library.gh_gram_pool_fwd(dummy, 7, 0, 0, 1, 256, 64, 32, dummy, 0, 1, 0, 0, None) == _lib.GH_ERR_BAD_ARG
+    assert library.gh_attn_head_bwd_workspace(4, 3, 64) == 2 * 4 * 64 + 3 * 4 * 3 * 64
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setenv("GRAMHEAD_LIB", str(tmp_path / "nope.so"))
+    monkeypatch.setattr(_lib, "_LIB", None)
+    with pytest.raises(_lib.GramHeadError, match="no CPU or PyTorch fallback"):
+        _lib.lib()

@@ -1,0 +1,348 @@
+"""GPU bring-up / diagnostics: each case runs in its own process (a device trap poisons the CUDA context) and prints
+normwise errors against the fp64 oracle. Usage on a B200:  python tools/gpu_bringup.py [case ...]   (default: all)"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+CASES = {}
+
+
+def case(fn):
+    CASES[fn.__name__] = fn
+    return fn
+
+
+def _np(t):
+    return t.detach().float().cpu().numpy()
+
+
+def _report_dev_error():
+    from heuristique_style_transfer_code_b200 import _lib
+    try:
+        print("   device error record:", _lib.last_device_error())
+    except Exception as e:  # context may be dead
+        print("   (could not read device error record:", e, ")")
+
+
+def _pool_case(B, C, HW, g, ksplit=0, dtype="f32", relu=True, seed=0):
+    import numpy as np
+    import torch
+    from heuristique_style_transfer_code_b200 import ops
+    from oracle import head_fp64 as O
+    torch.manual_seed(seed)
+    x = torch.randn(B, C, HW, device="cuda")
+    if relu:
+        x = torch.relu(x)
+    if dtype == "bf16":
+        x = x.bfloat16()
+    desc = torch.full((B, 2, g * g), float("nan"), device="cuda")
+    ops.KSPLIT = ksplit
+    ops.gram_pool_fwd_(x, g, desc, 1)
+    torch.cuda.synchronize()
+    got = _np(desc[:, 1])
+    xf = _np(x)
+    exact = O.descriptors([xf], g)[:, 0]
+    rounded = O.descriptors([xf], g, operand_rounding="bf16")[:, 0]
+    e1, e2 = O.rel_err(got, exact), O.rel_err(got, rounded)
+    untouched = bool(torch.isnan(desc[:, 0]).all())
+    print(f"pool B={B} C={C} HW={HW} g={g} ksplit={ksplit} {dtype}: rel_err vs fp64={e1:.3e} vs bf16-operand fp64={e2:.3e}"
+          f" other-slice-untouched={untouched}")
+    if not (e2 < 1e-4):
+        d = np.abs(got - rounded).reshape(B, g, g)
+        r = np.abs(rounded).reshape(B, g, g)
+        print("   per-image max abs err:", d.reshape(B, -1).max(1)[:8], " ref max:", r.reshape(B, -1).max(1)[:8])
+        blk = max(1, g // 8)
+        m = d[0].reshape(g // blk, blk, g // blk, blk).max(axis=(1, 3))
+        print("   image0 coarse error map (rows x cols of pooled matrix):")
+        for row in m:
+            print("    ", " ".join(f"{v:9.2e}" for v in row))
+        print("   got[0,:4,:4]=\n", got.reshape(B, g, g)[0, :4, :4], "\n   ref[0,:4,:4]=\n", rounded.reshape(B, g, g)[0, :4, :4])
+    return e1 < 1e-3 and e2 < 1e-4 and untouched
+
+
+@case
+def fwd_min():
+    """Smallest useful shapes: one K block, then several."""
+    ok = _pool_case(1, 256, 64, 32, ksplit=1)
+    ok &= _pool_case(1, 256, 128, 32, ksplit=1)
+    ok &= _pool_case(2, 256, 3136, 32, ksplit=1)
+    return ok
+
+
+@case
+def fwd_shapes():
+    ok = True
+    ok &= _pool_case(3, 512, 784, 32, ksplit=1)
+    ok &= _pool_case(2, 1024, 196, 32, ksplit=1)
+    ok &= _pool_case(2, 2048, 49, 32, ksplit=1)
+    ok &= _pool_case(5, 256, 3136, 32, ksplit=0)
+    ok &= _pool_case(5, 256, 3136, 32, ksplit=4)
+    ok &= _pool_case(3, 512, 784, 32, ksplit=3)
+    ok &= _pool_case(2, 256, 3136, 32, ksplit=1, dtype="bf16")
+    ok &= _pool_case(2, 1024, 196, 8, ksplit=1)       # k = 128
+    ok &= _pool_case(2, 256, 100, 64, ksplit=1)       # k = 4, HW tail
+    ok &= _pool_case(300, 256, 256, 32, ksplit=1)     # more units than CTAs (persistent loop, phase wrap)
+    return ok
+
+
+@case
+def fwd_dense():
+    import torch
+    from heuristique_style_transfer_code_b200 import ops
+    from oracle import head_fp64 as O
+    ok = True
+    for (B, C, HW, ks) in [(1, 64, 3136, 1), (2, 256, 784, 1), (2, 512, 196, 1), (1, 64, 3136, 0), (2, 320, 100, 1)]:
+        torch.manual_seed(0)
+        x = torch.relu(torch.randn(B, C, HW, device="cuda"))
+        ops.KSPLIT = ks
+        G = ops.gram_dense_fwd(x)
+        torch.cuda.synchronize()
+        ref = O.gram(O.bf16_round(_np(x)))
+        e = O.rel_err(_np(G), ref)
+        sym = float((G - G.transpose(1, 2)).abs().max())
+        print(f"dense B={B} C={C} HW={HW} ksplit={ks}: rel_err vs bf16-operand fp64={e:.3e} max|G-G^T|={sym:.3e}")
+        ok &= e < 1e-4
+    return ok
+
+
+@case
+def attn_fwd_bwd():
+    import numpy as np
+    import torch
+    from heuristique_style_transfer_code_b200 import ops
+    from oracle import head_fp64 as O
+    ok = True
+    for (B, L, g, nc) in [(5, 3, 8, 4), (33, 3, 32, 4), (4, 1, 16, 3), (7, 4, 8, 10)]:
+        E = g * g
+        torch.manual_seed(0)
+        desc = torch.randn(B, L, E, device="cuda") * 2.0
+        mha = torch.nn.MultiheadAttention(E, 1).cuda()
+        lin = torch.nn.Linear(E, nc).cuda()
+        with torch.no_grad():
+            mha.in_proj_bias.normal_(0, 0.1); mha.out_proj.bias.normal_(0, 0.1)
+        ps = [mha.in_proj_weight, mha.in_proj_bias, mha.out_proj.weight, mha.out_proj.bias, lin.weight, lin.bias]
+        d = desc.clone().requires_grad_(True)
+        emb, logits = ops.attention_head(d, *ps)
+        labels = torch.arange(B, device="cuda") % nc
+        w = torch.randn(B, E, device="cuda") * 0.01
+        loss = torch.nn.functional.cross_entropy(logits, labels) + (emb * w).sum()
+        loss.backward()
+        torch.cuda.synchronize()
+        params = dict(in_proj_weight=_np(ps[0]), in_proj_bias=_np(ps[1]), out_proj_weight=_np(ps[2]),
+                      out_proj_bias=_np(ps[3]), classifier_weight=_np(ps[4]), classifier_bias=_np(ps[5]))
+        c = O.attention_forward(_np(desc), *[params[k] for k in ("in_proj_weight", "in_proj_bias", "out_proj_weight",
+                                                                  "out_proj_bias", "classifier_weight", "classifier_bias")])
+        _, dl = O.cross_entropy(c["logits"], labels.cpu().numpy())
+        gr = O.attention_backward(c, params, dl, _np(w))
+        errs = dict(emb=O.rel_err(_np(emb), c["emb"]), logits=O.rel_err(_np(logits), c["logits"]),
+                    d_desc=O.rel_err(_np(d.grad), gr["d_desc"]),
+                    dW_in=O.rel_err(_np(ps[0].grad), gr["in_proj_weight"]), db_in=O.rel_err(_np(ps[1].grad), gr["in_proj_bias"]),
+                    dW_out=O.rel_err(_np(ps[2].grad), gr["out_proj_weight"]), db_out=O.rel_err(_np(ps[3].grad), gr["out_proj_bias"]),
+                    dW_c=O.rel_err(_np(ps[4].grad), gr["classifier_weight"]), db_c=O.rel_err(_np(ps[5].grad), gr["classifier_bias"]))
+        print(f"attn B={B} L={L} E={E} nc={nc}: " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()))
+        ok &= all(v < 2e-5 for v in errs.values())
+    return ok
+
+
+def _bwd_pool_case(B, C, HW, g, dtype="f32"):
+    import torch
+    from heuristique_style_transfer_code_b200 import ops
+    from oracle import head_fp64 as O
+    torch.manual_seed(0)
+    x = torch.relu(torch.randn(B, C, HW, device="cuda"))
+    if dtype == "bf16":
+        x = x.bfloat16()
+    dd = torch.randn(B, 2, g * g, device="cuda")
+    df = ops.gram_pool_bwd(x, g, dd, 1)
+    torch.cuda.synchronize()
+    ref = O.gram_pool_backward(_np(x), g, _np(dd[:, 1]))
+    e = O.rel_err(_np(df), ref)
+    print(f"pool-bwd B={B} C={C} HW={HW} g={g} {dtype}: rel_err vs fp64={e:.3e}")
+    return e < 6e-3
+
+
+@case
+def bwd_pool():
+    ok = _bwd_pool_case(1, 256, 128, 32)
+    ok &= _bwd_pool_case(2, 256, 3136, 32)
+    ok &= _bwd_pool_case(2, 512, 784, 32)
+    ok &= _bwd_pool_case(2, 1024, 196, 32)
+    ok &= _bwd_pool_case(2, 2048, 49, 32)
+    ok &= _bwd_pool_case(2, 256, 3136, 32, dtype="bf16")
+    ok &= _bwd_pool_case(40, 256, 784, 32)
+    return ok
+
+
+@case
+def bwd_dense():
+    import torch
+    from heuristique_style_transfer_code_b200 import ops
+    from oracle import head_fp64 as O
+    ok = True
+    for (B, C, HW) in [(1, 64, 3136), (2, 256, 196), (1, 512, 100)]:
+        torch.manual_seed(0)
+        x = torch.relu(torch.randn(B, C, HW, device="cuda"))
+        dg = torch.randn(B, C, C, device="cuda")
+        df = ops.gram_dense_bwd(x, dg)
+        torch.cuda.synchronize()
+        e = O.rel_err(_np(df), O.gram_dense_backward(_np(x), _np(dg)))
+        print(f"dense-bwd B={B} C={C} HW={HW}: rel_err vs fp64={e:.3e}")
+        ok &= e < 6e-3
+    return ok
+
+
+@case
+def generic_pool():
+    import torch
+    from heuristique_style_transfer_code_b200 import ops
+    from oracle import head_fp64 as O
+    ok = True
+    for (B, C, HW, g) in [(2, 256, 196, 24), (2, 64, 100, 7)]:
+        torch.manual_seed(0)
+        x = torch.relu(torch.randn(B, C, HW, device="cuda")).requires_grad_(True)
+        desc = ops.style_descriptor([x], g)
+        w = torch.randn_like(desc)
+        (desc * w).sum().backward()
+        torch.cuda.synchronize()
+        ref = O.descriptors([O.bf16_round(_np(x))], g)
+        e = O.rel_err(_np(desc), ref)
+        eb = O.rel_err(_np(x.grad), O.gram_pool_backward(_np(x), g, _np(w[:, 0])))
+        print(f"generic-bins B={B} C={C} HW={HW} g={g}: fwd rel_err={e:.3e} bwd rel_err={eb:.3e}")
+        ok &= e < 1e-4 and eb < 6e-3
+    return ok
+
+
+@case
+def module_parity():
+    """Whole drop-in module vs the fp32 torch port of the reference, both on the GPU, train-mode BN."""
+    import torch
+    from torchvision import models
+    from heuristique_style_transfer_code_b200 import TruncatedResNet50_for_test
+    from oracle.torch_port import PortModel
+    from oracle import head_fp64 as O
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ok = True
+    for mode in ("train", "eval"):
+        torch.manual_seed(0)
+        ours = TruncatedResNet50_for_test(models.resnet50(weights=None), 7, 4, 32, device="cuda")
+        port = PortModel(models.resnet50(weights=None), 7, 4, 32, device="cuda", return_embeddings=True)
+        port.load_state_dict(ours.state_dict())
+        getattr(ours, mode)(); getattr(port, mode)()
+        torch.manual_seed(1)
+        x = torch.randn(8, 3, 224, 224, device="cuda")
+        y = torch.randint(0, 4, (8,), device="cuda")
+        e1, l1 = ours(x)
+        e2, l2 = port(x)
+        loss1 = torch.nn.functional.cross_entropy(l1, y); loss1.backward()
+        loss2 = torch.nn.functional.cross_entropy(l2, y); loss2.backward()
+        torch.cuda.synchronize()
+        print(f"module[{mode}]: emb rel={O.rel_err(_np(e1), _np(e2)):.3e} logits rel={O.rel_err(_np(l1), _np(l2)):.3e} "
+              f"argmax equal={bool((l1.argmax(1) == l2.argmax(1)).all())} loss {loss1.item():.6f} vs {loss2.item():.6f}")
+        worst = 0.0
+        for (n, p1), (_, p2) in zip(ours.named_parameters(), port.named_parameters()):
+            if p1.grad is None or p2.grad is None:
+                print("   missing grad:", n, p1.grad is None, p2.grad is None)
+                ok = False
+                continue
+            e = O.rel_err(_np(p1.grad), _np(p2.grad))
+            worst = max(worst, e)
+            if n.startswith(("attention", "classifier")) or n in ("truncated_encoder.0.weight",):
+                print(f"   grad {n}: rel={e:.3e}")
+        print(f"   worst param-grad rel err over all {len(list(ours.parameters()))} params: {worst:.3e}")
+        ok &= bool((l1.argmax(1) == l2.argmax(1)).all())
+    return ok
+
+
+@case
+def timing():
+    """Kernel-only timings at batch 256 (inputs 0.2-0.8 GB each: larger than the 126 MB L2)."""
+    import json
+    import torch
+    from heuristique_style_transfer_code_b200 import ops
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+    B, g = 256, 32
+    for (C, HW) in [(256, 3136), (512, 784), (1024, 196)]:
+        x = torch.relu(torch.randn(B, C, HW, device="cuda"))
+        desc = torch.empty(B, 3, g * g, device="cuda")
+        dd = torch.randn(B, 3, g * g, device="cuda")
+        for ks in (0, 1, 2, 4, 7):
+            ops.KSPLIT = ks
+            for _ in range(3):
+                ops.gram_pool_fwd_(x, g, desc, 0)
+            torch.cuda.synchronize()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            n = 10
+            ev[0].record()
+            for _ in range(n):
+                ops.gram_pool_fwd_(x, g, desc, 0)
+            ev[1].record(); torch.cuda.synchronize()
+            ms = ev[0].elapsed_time(ev[1]) / n
+            by = B * C * HW * 4 + B * g * g * 4
+            fl = B * C * (C + 1) * HW
+            print(f"fwd C={C} HW={HW} ksplit={ks}: {ms*1e3:8.1f} us  {by/ms/1e6:8.1f} GB/s ({by/ms/1e6/peaks['hbm_gbs']:.2f} of HBM)"
+                  f"  {fl/ms/1e9:8.1f} TFLOP/s sym ({fl/ms/1e9/peaks['bf16_tflops']:.2f} of tensor)")
+        ops.KSPLIT = 0
+        for _ in range(3):
+            ops.gram_pool_bwd(x, g, dd, 0)
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        n = 10
+        ev[0].record()
+        for _ in range(n):
+            ops.gram_pool_bwd(x, g, dd, 0)
+        ev[1].record(); torch.cuda.synchronize()
+        ms = ev[0].elapsed_time(ev[1]) / n
+        by = 2 * B * C * HW * 4
+        fl = 2 * B * C * C * HW
+        print(f"bwd C={C} HW={HW}: {ms*1e3:8.1f} us  {by/ms/1e6:8.1f} GB/s ({by/ms/1e6/peaks['hbm_gbs']:.2f} of HBM)"
+              f"  {fl/ms/1e9:8.1f} TFLOP/s ({fl/ms/1e9/peaks['bf16_tflops']:.2f} of tensor)")
+        # torch reference ops on the same GPU (fp32 bmm + div + pool), for scale
+        xf = x
+        for _ in range(2):
+            G = torch.bmm(xf, xf.transpose(1, 2)).div(HW); P = torch.nn.functional.adaptive_avg_pool2d(G, (g, g))
+        torch.cuda.synchronize()
+        ev[0].record()
+        for _ in range(3):
+            G = torch.bmm(xf, xf.transpose(1, 2)).div(HW); P = torch.nn.functional.adaptive_avg_pool2d(G, (g, g))
+        ev[1].record(); torch.cuda.synchronize()
+        print(f"torch fp32 bmm+div+pool C={C} HW={HW}: {ev[0].elapsed_time(ev[1])/3*1e3:8.1f} us")
+        del x, desc, dd, G, P
+    return True
+
+
+def main():
+    names = sys.argv[1:] or list(CASES)
+    if len(names) == 1 and os.environ.get("GH_BRINGUP_CHILD") == "1":
+        name = names[0]
+        t0 = time.time()
+        try:
+            ok = CASES[name]()
+        except Exception as e:
+            import traceback
+            traceback.print_exc()
+            _report_dev_error()
+            ok = False
+        print(f"[{name}] {'PASS' if ok else 'FAIL'} ({time.time()-t0:.1f}s)", flush=True)
+        sys.exit(0 if ok else 1)
+    results = {}
+    for name in names:
+        print(f"===== {name} =====", flush=True)
+        env = dict(os.environ, GH_BRINGUP_CHILD="1")
+        try:
+            rc = subprocess.run([sys.executable, os.path.abspath(__file__), name], env=env, timeout=420).returncode
+        except subprocess.TimeoutExpired:
+            rc = "timeout"
+        results[name] = rc
+    print("SUMMARY", results, flush=True)
+    sys.exit(0 if all(v == 0 for v in results.values()) else 1)
+
+
+if __name__ == "__main__":
+    main()
