@@ -1,0 +1,363 @@
+"""Benchmark of the Gram + attention classifier on B200 (contract: one JSON line on stdout from rank 0).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): truncated ResNet50 (truncate_layer 7) + Gram + attention, random-init weights,
+synthetic batch of 256 images per GPU at 224x224, 4 classes, inference (eval mode, no_grad). A step is one forward of
+the whole model on one batch: cuDNN encoder (left to the reference's path, timed separately in `breakdown`) followed by
+the sm_100a head (3 pooled-Gram launches + attention/classifier). Multi-GPU: the batch is sharded, 256 images per rank
+(weak scaling); the only collective is the all-gather of logits and embeddings, inside the timed region.
+
+  value      images/s with the batch resident in HBM (154 MB of fp32 images per rank: larger than the 126 MB L2)
+  e2e        same through the public call model(x_host): pinned host batch -> H2D -> forward -> logits+embeddings D2H
+  roofline   the library kernel that takes the most time inside the timed steps, measured live with CUDA events
+  cpu_baseline  the reference's CPU path (oracle/torch_port.py, op-for-op fp32 port) on this box's host cores, bounded sample
+  train      BASELINE.json configs[2]: full training step (forward + Gram backward + AdamW), global batch 512 sharded
+             over the N ranks with DDP/NCCL (strong scaling); reported as an extra object, not as `value`
+
+--impl reference times the reference's own CPU implementation of the same forward (the oracle port: /root/reference
+is not on the GPU box) with every host thread, on bounded samples of the same batch.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+TRUNC, NUM_CLASSES, GRAM_SIZE, IMAGE = 7, 4, 32, 224
+WORKLOAD = ("configs[1]: truncated ResNet50 (7 children) + Gram + attention, random init, synthetic batch 256/GPU at "
+            "224x224, 4 classes, inference")
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p["hbm_gbs"], tensor_tflops=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    tensor_tflops_burst=p["bf16_tflops"], source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, tensor_tflops=1400.0, tensor_tflops_burst=1590.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        return False
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, flag in zip(names, r[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def timed_region(fn, steps, device, dist_mod):
+    """barrier + synchronize, CUDA events on the current stream around exactly `steps` calls, max over ranks (ms)."""
+    dist_mod.barrier(device)
+    torch.cuda.synchronize(device)
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(steps):
+        fn()
+    end.record()
+    torch.cuda.synchronize(device)
+    dist_mod.barrier(device)
+    return dist_mod.max_over_ranks(start.elapsed_time(end), device)
+
+
+def summarise_profile(records, peaks):
+    """records: ops.PROFILE entries -> per-kernel averages and the roofline object of the dominant one."""
+    agg = {}
+    for name, work, s, e in records:
+        a = agg.setdefault(name, dict(ms=0.0, n=0, work=work))
+        a["ms"] += s.elapsed_time(e)
+        a["n"] += 1
+    kernels = {}
+    for name, a in agg.items():
+        ms = a["ms"] / a["n"]
+        kernels[name] = dict(avg_us=round(ms * 1e3, 2), launches=a["n"], total_ms=round(a["ms"], 3),
+                             GBps=round(a["work"]["bytes"] / ms / 1e6, 1), TFLOPs=round(a["work"]["flops"] / ms / 1e9, 1))
+    if not agg:
+        return kernels, None
+    top = max(agg, key=lambda k: agg[k]["ms"])
+    a = agg[top]
+    ms = a["ms"] / a["n"]
+    t_hbm = a["work"]["bytes"] / (peaks["hbm_gbs"] * 1e9)
+    t_tc = a["work"]["flops"] / (peaks["tensor_tflops"] * 1e12)
+    if t_hbm >= t_tc:
+        ach, peak, unit, bound = a["work"]["bytes"] / ms / 1e6, peaks["hbm_gbs"], "GB/s", "hbm"
+    else:
+        ach, peak, unit, bound = a["work"]["flops"] / ms / 1e9, peaks["tensor_tflops"], "TFLOP/s", "tensor"
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.isfile(tpath):
+        traffic = json.load(open(tpath)).get(top)
+    roof = dict(kernel=top, bound=bound, achieved=round(ach, 1), peak=peak, unit=unit, frac=round(ach / peak, 4),
+                traffic=traffic, avg_launch_us=round(ms * 1e3, 2), algorithmic_bytes=a["work"]["bytes"],
+                algorithmic_flops=a["work"]["flops"], peak_source=peaks["source"],
+                share_of_library_time=round(a["ms"] / sum(v["ms"] for v in agg.values()), 3))
+    return kernels, roof
+
+
+def cpu_reference_forward(batch, sample, steps, warmup, threads):
+    """The reference's CPU path (oracle port), eval + no_grad, on `sample` images of the synthetic batch."""
+    from torchvision import models
+    from oracle.torch_port import PortModel
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    model = PortModel(models.resnet50(weights=None), TRUNC, NUM_CLASSES, GRAM_SIZE, device="cpu", return_embeddings=True)
+    model.eval()
+    torch.manual_seed(1)
+    x = torch.randn(sample, 3, IMAGE, IMAGE)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            model(x)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    return sample * len(times) / sum(times), sum(times) / len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = 16
+    ips, sec = cpu_reference_forward(256, sample, args.steps, max(args.warmup, 1), cores)
+    line = {"impl": "reference", "metric": "images/sec", "value": round(ips, 2), "unit": "images/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "CPU has no batch-256 budget: each step is a 16-image sample of the batch"},
+            "cpu_baseline": {"value": round(ips, 2), "unit": "images/s", "cores": cores, "kind": "port",
+                             "sample": f"{sample} images of the 256-image batch per step, {args.steps} steps, torch "
+                                       f"{torch.__version__} CPU fp32, {cores} threads (oracle/torch_port.py: the "
+                                       "reference's op sequence; /root/reference is not on this box)"},
+            "e2e": {"value": round(ips, 2), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    from torchvision import models
+    from heuristique_style_transfer_code_b200 import TruncatedResNet50, TruncatedResNet50_for_test, ops, _lib
+    from heuristique_style_transfer_code_b200 import distributed as D
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the head has no CPU path (use --impl reference for the CPU arm)")
+    _lib.lib()
+    rank, world, local, device = D.init_from_env()
+    if world != args.gpus and rank == 0:
+        print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch with torch.distributed.run", file=sys.stderr)
+    peaks = load_peaks()
+    B = args.batch_per_gpu
+
+    torch.manual_seed(0)
+    model = TruncatedResNet50_for_test(models.resnet50(weights=None), TRUNC, NUM_CLASSES, GRAM_SIZE, device=device)
+    model.eval()
+    torch.manual_seed(1 + rank)
+    x_host = torch.randn(B, 3, IMAGE, IMAGE).pin_memory()
+    x = x_host.to(device)
+    total = B * world
+
+    def infer_step():
+        with torch.no_grad():
+            emb, logits = model(x)
+            if world > 1:
+                logits = D.gather_rows(logits, total, world)
+                emb = D.gather_rows(emb, total, world)
+        return emb, logits
+
+    for _ in range(args.warmup):
+        infer_step()
+    ops.PROFILE = []
+    ops.LAUNCHES = 0
+    with ClockSampler(local) as clocks:
+        ms = timed_region(infer_step, args.steps, device, D)
+    records, ops.PROFILE = ops.PROFILE, None
+    launches = ops.LAUNCHES
+    kernels, roof = summarise_profile(records, peaks)
+    value = total * args.steps / (ms / 1e3)
+
+    # ---- breakdown: encoder alone, head alone (device resident, same batch) ----
+    with torch.no_grad():
+        _, stages = model._stage_activations(x)
+
+        def enc_only():
+            with torch.no_grad():
+                model._stage_activations(x)
+
+        def head_only():
+            with torch.no_grad():
+                d = ops.style_descriptor(stages, GRAM_SIZE)
+                ops.attention_head(d, model.attention.in_proj_weight, model.attention.in_proj_bias,
+                                   model.attention.out_proj.weight, model.attention.out_proj.bias,
+                                   model.classifier.weight, model.classifier.bias)
+        for _ in range(3):
+            enc_only(); head_only()
+        enc_ms = timed_region(enc_only, args.steps, device, D) / args.steps
+        head_ms = timed_region(head_only, args.steps, device, D) / args.steps
+    del stages
+
+    # ---- end to end through the public call: host batch in, logits + embeddings out ----
+    def e2e_step():
+        with torch.no_grad():
+            emb, logits = model(x_host)                 # forward() moves the pinned batch to self.device (H2D)
+            if world > 1:
+                logits = D.gather_rows(logits, total, world)
+                emb = D.gather_rows(emb, total, world)
+            return emb.cpu(), logits.cpu()              # D2H of the results (the synchronisation point, as upstream)
+
+    for _ in range(2):
+        e2e_step()
+    e2e_ms = timed_region(e2e_step, args.steps, device, D)
+    e2e_value = total * args.steps / (e2e_ms / 1e3)
+    h2d = B * 3 * IMAGE * IMAGE * 4
+    d2h = total * (GRAM_SIZE * GRAM_SIZE + NUM_CLASSES) * 4
+
+    # ---- configs[2]: training step, global batch 512 over the ranks (strong scaling), AdamW ----
+    train = None
+    if not args.skip_train:
+        del x
+        torch.cuda.empty_cache()
+        gb = args.train_global_batch
+        lo, hi = D.shard_bounds(gb, rank, world)
+        torch.manual_seed(0)
+        tmodel = TruncatedResNet50(models.resnet50(weights=None), TRUNC, NUM_CLASSES, GRAM_SIZE, device=device)
+        tmodel.train()
+        ddp = D.wrap_ddp(tmodel, device)
+        opt = torch.optim.AdamW(tmodel.parameters(), lr=1e-3)
+        crit = torch.nn.CrossEntropyLoss()
+        torch.manual_seed(100 + rank)
+        xt = torch.randn(hi - lo, 3, IMAGE, IMAGE, device=device)
+        yt = torch.randint(0, NUM_CLASSES, (hi - lo,), device=device)
+
+        def train_step():
+            opt.zero_grad(set_to_none=True)
+            loss = crit(ddp(xt), yt)
+            loss.backward()
+            opt.step()
+            return loss
+
+        tsteps = max(3, min(args.steps, args.train_steps))
+        for _ in range(3):
+            train_step()
+        ops.PROFILE = []
+        tms = timed_region(train_step, tsteps, device, D)
+        trec, ops.PROFILE = ops.PROFILE, None
+        tk, troof = summarise_profile(trec, peaks)
+        train = {"metric": "images/sec", "value": round(gb * tsteps / (tms / 1e3), 1), "unit": "images/s",
+                 "ms_per_step": round(tms / tsteps, 2), "steps": tsteps, "scaling": "strong",
+                 "config": {"workload": "configs[2]: full training step (forward + Gram/attention backward + cuDNN "
+                                        "backward + AdamW), train-mode BN, CE loss", "global_batch": gb,
+                            "per_gpu_batch": hi - lo, "optimizer": "AdamW(lr=1e-3)",
+                            "parallelism": f"ddp{world}" if world > 1 else "single"},
+                 "kernels": tk, "roofline": troof}
+        del xt, yt, tmodel, ddp, opt
+
+    if rank != 0:
+        return
+
+    cpu_base = None
+    if world == 1 and not args.skip_cpu:
+        cores = os.cpu_count() or 1
+        sample = 16
+        ips, sec = cpu_reference_forward(B, sample, 6, 2, cores)
+        cpu_base = {"value": round(ips, 2), "unit": "images/s", "cores": cores, "kind": "port",
+                    "sample": f"{sample} images of the batch per step, 6 steps after 2 warm-ups ({sec:.2f} s/step), torch "
+                              f"{torch.__version__} CPU fp32 eval/no_grad, {cores} threads, oracle/torch_port.py"}
+
+    line = {"metric": "images/sec", "value": round(value, 1), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": total, "per_gpu_batch": B, "image": IMAGE,
+                       "truncate_layer": TRUNC, "gram_matrix_size": GRAM_SIZE, "num_classes": NUM_CLASSES,
+                       "precision": "encoder: cuDNN fp32 (TF32 conv allowed, torch default); Gram: bf16 operands, fp32 "
+                                    "accumulate (tcgen05); attention/classifier: fp32",
+                       "l2_policy": "inputs larger than L2 (154 MB images, 210/105/51 MB stage activations per step)",
+                       "parallelism": f"batch-sharded x{world}, all_gather of logits+embeddings" if world > 1 else "single GPU"},
+            "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": round(e2e_ms / args.steps, 3)},
+            "gpu_launches": launches,
+            "roofline": roof,
+            "cpu_baseline": cpu_base,
+            "clocks": clocks.summary(),
+            "breakdown": {"encoder_cudnn_ms": round(enc_ms, 3), "head_ms": round(head_ms, 3),
+                          "head_images_per_s": round(B / (head_ms / 1e3), 1), "kernels": kernels},
+            "train": train}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--batch-per-gpu", type=int, default=256)
+    ap.add_argument("--train-global-batch", type=int, default=512)
+    ap.add_argument("--train-steps", type=int, default=10)
+    ap.add_argument("--skip-train", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -19,6 +19,7 @@ _P = c_void_p
 _SIGNATURES = {
     "gh_version": (c_int, []),
     "gh_sm_count": (c_int, []),
+    "gh_set_option": (c_int, [ctypes.c_char_p, c_int]),
     "gh_last_device_error": (c_int, [POINTER(c_uint)]),
     "gh_gram_pool_fwd": (c_int, [_P, c_int, c_longlong, c_longlong, c_int, c_int, c_int, c_int, _P, c_int, c_int,
                                   c_int, c_int, _P]),

@@ -8,11 +8,12 @@
 // Work decomposition
 //   unit      = (image b, 256x256 super-tile (I <= J) of the Gram, K-range kp of ksplit)
 //   CTA       = persistent, walks units blockIdx.x, +gridDim.x, ...
-//   warps 0-7 = producers: ld.global fp32/bf16 (coalesced along HW) -> cvt.rn.bf16x2 -> st.shared into the
-//               UMMA K-major SWIZZLE_128B layout (no separate cast pass over HBM, any HW, any pitch)
-//   warps 8-11= epilogue: tcgen05.ld -> in-register k x k block sums -> red.global.add into the descriptor
-//               (mirrored for off-diagonal 128-col blocks) or dense G stores
-//   warp 12   = TMEM owner + the single MMA-issuing thread
+//   producers = NPW (8 or 16) warps: ld.global fp32/bf16 (coalesced along HW) -> cvt.rn.bf16x2 -> st.shared into the
+//               UMMA K-major SWIZZLE_128B layout (no separate cast pass over HBM, any HW, any pitch); the loads of
+//               stage s+1 are issued before stage s is converted and stored (register double buffering)
+//   epilogue  = 4 warps: tcgen05.ld -> in-register k x k block sums -> descriptor (mirrored for off-diagonal
+//               128-col blocks; plain stores when each element has one writer, red.global.add otherwise) or dense G
+//   MMA       = 1 warp: TMEM owner + the single MMA-issuing thread
 //   smem ring = 6 stages of [256 rows][64 k] bf16 (32 KB). A diagonal super-tile consumes one stage per k-block
 //               (A and B tiles are the same rows), an off-diagonal one consumes two (I rows, then J rows).
 //   TMEM      = 512 columns: acc0 = rows 0-127 of I x 256 cols, acc1 = rows 128-255 of I x (128 | 256) cols.
@@ -22,11 +23,6 @@
 
 namespace gh {
 
-constexpr int kGfProducerWarps = 8;
-constexpr int kGfProducerThreads = kGfProducerWarps * 32;
-constexpr int kGfEpiWarp0 = 8;
-constexpr int kGfMmaWarp = 12;
-constexpr int kGfThreads = 13 * 32;
 constexpr int kGfStages = 6;
 constexpr uint32_t kGfStageRows = 256;
 constexpr uint32_t kGfStageBytes = kGfStageRows * kRowBytes;   // 32 KB
@@ -49,7 +45,7 @@ struct GramFwdParams {
   float* out;             // POOL: (B, L, g*g) slice base for this stage; DENSE: (B, C, C)
   long long out_img_stride;
   float scale;
-  int use_atomics;        // DENSE only (POOL always accumulates with red.add into a zeroed buffer)
+  int use_atomics;        // outputs meet in red.global.add (ksplit > 1, or pool factor > 32): buffer pre-zeroed
 };
 
 struct GramUnit {
@@ -72,96 +68,134 @@ __device__ __forceinline__ GramUnit gram_decode_unit(const GramFwdParams& p, int
 }
 
 // ---- producers ----------------------------------------------------------------------------------------------------
-// One stage = rows [blk*256, blk*256+256) x k in [kb*64, kb*64+64). fp32 source, 16 B aligned rows.
-// 16 threads cover one row (64 fp32 = 256 B, one float4 each); a warp covers two rows per pass; 16 passes.
-__device__ __forceinline__ void gram_fill_stage_f32_vec(const GramFwdParams& p, int b, int blk, int kb, uint32_t stage_smem,
-                                                        int tid) {
-  const int half = tid >> 4, q = tid & 15;
-  const int k = kb * 64 + q * 4;
-  const bool kvalid = k < p.HW;   // HW % 4 == 0 on this path, so k+3 < HW too
-  const float* base = reinterpret_cast<const float*>(p.F) + (long long)b * p.img_stride + k;
-  const int c0 = blk * 256 + half;
-  float4 v[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int c = c0 + i * 16;
-    if (kvalid && c < p.C) v[i] = ldg_stream_f4(base + (long long)c * p.row_stride);
-    else v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const uint32_t r = (uint32_t)(half + i * 16);
-    sts_u2(stage_smem + sw128_off(r, (uint32_t)(q * 4)), pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
-  }
+// One stage = rows [blk*256, blk*256+256) x k in [kb*64, kb*64+64) of image b.
+// 16 threads cover one row (64 elements, 4 each); NT producer threads cover NT/16 rows per pass, 4096/NT passes.
+// Loading (global -> registers) and storing (registers -> swizzled smem) are separate steps so that the loads of the
+// NEXT stage are in flight while the current one is converted and stored (register double buffering): the memory
+// pipe never drains between stages, units or images.
+struct GfItem {
+  int u, kb, h, nblk;
+  GramUnit w;
+};
+__device__ __forceinline__ bool gf_item_first(GfItem& it, const GramFwdParams& p) {
+  it.u = blockIdx.x;
+  if (it.u >= p.total_units) return false;
+  it.w = gram_decode_unit(p, it.u);
+  it.nblk = (it.w.I == it.w.J) ? 1 : 2;
+  it.kb = it.w.kb0;
+  it.h = 0;
+  return true;
 }
-// Any HW / pitch / alignment: scalar loads with per-element bounds.
-__device__ __forceinline__ void gram_fill_stage_f32_scalar(const GramFwdParams& p, int b, int blk, int kb,
-                                                           uint32_t stage_smem, int tid) {
-  const int half = tid >> 4, q = tid & 15;
-  const int k = kb * 64 + q * 4;
-  const float* base = reinterpret_cast<const float*>(p.F) + (long long)b * p.img_stride + k;
-  const int c0 = blk * 256 + half;
-#pragma unroll 4
-  for (int i = 0; i < 16; ++i) {
-    const int c = c0 + i * 16;
-    float x[4] = {0.f, 0.f, 0.f, 0.f};
-    if (c < p.C) {
-      const float* rp = base + (long long)c * p.row_stride;
+__device__ __forceinline__ bool gf_item_next(GfItem& it, const GramFwdParams& p) {
+  if (++it.h < it.nblk) return true;
+  it.h = 0;
+  if (++it.kb < it.w.kb1) return true;
+  it.u += gridDim.x;
+  if (it.u >= p.total_units) return false;
+  it.w = gram_decode_unit(p, it.u);
+  it.nblk = (it.w.I == it.w.J) ? 1 : 2;
+  it.kb = it.w.kb0;
+  return true;
+}
+
+// SRC: 0 = fp32 vector (16 B aligned rows, HW % 4 == 0), 1 = fp32 scalar (anything), 2 = bf16 vector (8 B), 3 = bf16 scalar.
+// Register image of one thread's share of a stage: NL x 4 elements, already packed to bf16x2 pairs for SRC >= 1.
+template <int SRC, int NL>
+struct GfRegs {
+  float4 f[SRC == 0 ? NL : 1];
+  uint2 h[SRC == 0 ? 1 : NL];
+};
+
+template <int SRC, int NT>
+__device__ __forceinline__ void gf_load(const GramFwdParams& p, const GfItem& it, GfRegs<SRC, 4096 / NT>& r, int tid) {
+  constexpr int NL = 4096 / NT, RPP = NT / 16;
+  const int sub = tid >> 4, q = tid & 15;
+  const int k = it.kb * 64 + q * 4;
+  const int blk = it.h == 0 ? it.w.I : it.w.J;
+  const int c0 = blk * 256 + sub;
+  if (SRC == 0) {
+    const bool kvalid = k < p.HW;   // HW % 4 == 0 on this path, so k+3 < HW too
+    const float* base = reinterpret_cast<const float*>(p.F) + (long long)it.w.b * p.img_stride + k;
 #pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if (k + e < p.HW) x[e] = __ldg(rp + e);
+    for (int i = 0; i < NL; ++i) {
+      const int c = c0 + i * RPP;
+      if (kvalid && c < p.C) r.f[i] = ldg_stream_f4(base + (long long)c * p.row_stride);
+      else r.f[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    const uint32_t r = (uint32_t)(half + i * 16);
-    sts_u2(stage_smem + sw128_off(r, (uint32_t)(q * 4)), pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]));
-  }
-}
-// bf16 source, rows 8 B aligned (HW % 4 == 0): same thread map, 8 B per thread.
-__device__ __forceinline__ void gram_fill_stage_bf16_vec(const GramFwdParams& p, int b, int blk, int kb,
-                                                         uint32_t stage_smem, int tid) {
-  const int half = tid >> 4, q = tid & 15;
-  const int k = kb * 64 + q * 4;
-  const bool kvalid = k < p.HW;
-  const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(p.F) + (long long)b * p.img_stride + k;
-  const int c0 = blk * 256 + half;
-  uint2 v[16];
+  } else if (SRC == 1) {
+    const float* base = reinterpret_cast<const float*>(p.F) + (long long)it.w.b * p.img_stride + k;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int c = c0 + i * 16;
-    if (kvalid && c < p.C) v[i] = ldg_stream_u2(base + (long long)c * p.row_stride);
-    else v[i] = make_uint2(0u, 0u);
-  }
+    for (int i = 0; i < NL; ++i) {
+      const int c = c0 + i * RPP;
+      float x[4] = {0.f, 0.f, 0.f, 0.f};
+      if (c < p.C) {
+        const float* rp = base + (long long)c * p.row_stride;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const uint32_t r = (uint32_t)(half + i * 16);
-    sts_u2(stage_smem + sw128_off(r, (uint32_t)(q * 4)), v[i].x, v[i].y);
-  }
-}
-__device__ __forceinline__ void gram_fill_stage_bf16_scalar(const GramFwdParams& p, int b, int blk, int kb,
-                                                            uint32_t stage_smem, int tid) {
-  const int half = tid >> 4, q = tid & 15;
-  const int k = kb * 64 + q * 4;
-  const unsigned short* base = reinterpret_cast<const unsigned short*>(p.F) + (long long)b * p.img_stride + k;
-  const int c0 = blk * 256 + half;
-#pragma unroll 4
-  for (int i = 0; i < 16; ++i) {
-    const int c = c0 + i * 16;
-    unsigned int x[4] = {0u, 0u, 0u, 0u};
-    if (c < p.C) {
-      const unsigned short* rp = base + (long long)c * p.row_stride;
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if (k + e < p.HW) x[e] = __ldg(rp + e);
+        for (int e = 0; e < 4; ++e)
+          if (k + e < p.HW) x[e] = __ldg(rp + e);
+      }
+      r.h[i] = make_uint2(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]));
     }
-    const uint32_t r = (uint32_t)(half + i * 16);
-    sts_u2(stage_smem + sw128_off(r, (uint32_t)(q * 4)), x[0] | (x[1] << 16), x[2] | (x[3] << 16));
+  } else if (SRC == 2) {
+    const bool kvalid = k < p.HW;
+    const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(p.F) + (long long)it.w.b * p.img_stride + k;
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+      const int c = c0 + i * RPP;
+      if (kvalid && c < p.C) r.h[i] = ldg_stream_u2(base + (long long)c * p.row_stride);
+      else r.h[i] = make_uint2(0u, 0u);
+    }
+  } else {
+    const unsigned short* base = reinterpret_cast<const unsigned short*>(p.F) + (long long)it.w.b * p.img_stride + k;
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+      const int c = c0 + i * RPP;
+      unsigned int x[4] = {0u, 0u, 0u, 0u};
+      if (c < p.C) {
+        const unsigned short* rp = base + (long long)c * p.row_stride;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (k + e < p.HW) x[e] = __ldg(rp + e);
+      }
+      r.h[i] = make_uint2(x[0] | (x[1] << 16), x[2] | (x[3] << 16));
+    }
   }
+}
+
+template <int SRC, int NT>
+__device__ __forceinline__ void gf_store(const GramFwdParams& p, const GfItem& it, const GfRegs<SRC, 4096 / NT>& r,
+                                         uint32_t stage_smem, int tid) {
+  constexpr int NL = 4096 / NT, RPP = NT / 16;
+  const int sub = tid >> 4, q = tid & 15;
+  // a 16-wide k-step that lies entirely beyond HW is never issued to the tensor core, so it need not be written
+  if (it.kb * 64 + (q >> 2) * 16 >= p.HW) return;
+#pragma unroll
+  for (int i = 0; i < NL; ++i) {
+    const uint32_t row = (uint32_t)(sub + i * RPP);
+    const uint32_t addr = stage_smem + sw128_off(row, (uint32_t)(q * 4));
+    if (SRC == 0) sts_u2(addr, pack_bf16x2(r.f[i].x, r.f[i].y), pack_bf16x2(r.f[i].z, r.f[i].w));
+    else sts_u2(addr, r.h[i].x, r.h[i].y);
+  }
+}
+
+template <int SRC, int NT>
+__device__ __forceinline__ void gf_publish(const GramFwdParams& p, const GfItem& it, const GfRegs<SRC, 4096 / NT>& r,
+                                           uint32_t smem_base, uint32_t bar_full, uint32_t bar_empty, uint32_t& stage,
+                                           uint32_t& phase, int tid, int lane) {
+  mbar_wait(bar_empty + 8 * stage, phase ^ 1u, 100u + stage);
+  gf_store<SRC, NT>(p, it, r, smem_base + stage * kGfStageBytes, tid);
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar_full + 8 * stage);
+  if (++stage == kGfStages) { stage = 0; phase ^= 1u; }
 }
 
 // ---- epilogue -----------------------------------------------------------------------------------------------------
 // One 32-lane x 32-column chunk of an accumulator. Thread = Gram row c_row, v[j] = G[c_row][c_col0 + j] (unscaled).
 template <int KP>
 __device__ __forceinline__ void gram_epi_pool_chunk(const float (&v)[32], int c_row, int c_col0, int C, int g,
-                                                    float scale, float* __restrict__ outp, bool mirror, int lane) {
+                                                    float scale, float* __restrict__ outp, bool mirror, bool atomics,
+                                                    int lane) {
   constexpr int CW = KP < 32 ? KP : 32;   // columns summed in-thread per value
   constexpr int NC = 32 / CW;             // values this chunk yields per row
   constexpr int LK = KP < 32 ? KP : 32;   // rows (lanes) summed by shuffles
@@ -188,8 +222,13 @@ __device__ __forceinline__ void gram_epi_pool_chunk(const float (&v)[32], int c_
       if (col < C) {
         const int pj = col / KP;
         const float val = s[j] * scale;
-        red_add_f32(outp + pi * g + pj, val);
-        if (mirror) red_add_f32(outp + pj * g + pi, val);
+        if (atomics) {
+          red_add_f32(outp + pi * g + pj, val);
+          if (mirror) red_add_f32(outp + pj * g + pi, val);
+        } else {
+          outp[pi * g + pj] = val;
+          if (mirror) outp[pj * g + pi] = val;
+        }
       }
     }
   }
@@ -223,9 +262,15 @@ __device__ __forceinline__ void gram_epi_dense_chunk(const float (&v)[32], int c
   }
 }
 
-// SRC: 0 = fp32 vector, 1 = fp32 scalar, 2 = bf16 vector, 3 = bf16 scalar.  KP = pool factor (POOL) or 0 (DENSE).
-template <int SRC, int KP>
-__global__ void __launch_bounds__(kGfThreads, 1) gram_fwd_kernel(const GramFwdParams p) {
+// SRC: see gf_load.  KP = pool factor (POOL) or 0 (DENSE).  NPW = producer warps (8 or 16).
+// Warp roles: [0, NPW) producers, [NPW, NPW+4) epilogue (NPW % 4 == 0 so warp % 4 is the TMEM lane quarter). The first
+// epilogue warp also owns TMEM and issues the MMAs of a unit before joining its epilogue: with one accumulator set in
+// TMEM (384-512 of the 512 columns) the two phases of a unit cannot overlap anyway, and NPW + 4 warps (a multiple of
+// the 4 SM sub-partitions) leaves every thread 96 (NPW = 16) / 168 (NPW = 8) registers for the double-buffered loads.
+template <int SRC, int KP, int NPW>
+__global__ void __launch_bounds__((NPW + 4) * 32, 1) gram_fwd_kernel(const GramFwdParams p) {
+  constexpr int NT = NPW * 32;
+  constexpr int kEpiWarp0 = NPW, kMmaWarp = NPW;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = smem_base + kGfStages * kGfStageBytes;
@@ -240,97 +285,91 @@ __global__ void __launch_bounds__(kGfThreads, 1) gram_fwd_kernel(const GramFwdPa
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kGfStages; ++s) {
-      mbar_init(bar_full + 8 * s, kGfProducerWarps);
+      mbar_init(bar_full + 8 * s, NPW);
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_tfull, 1);
     mbar_init(bar_tempty, 4);
     mbar_fence_init();
   }
-  if (warp == kGfMmaWarp) tmem_alloc(tmem_slot, kGfTmemCols);
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, kGfTmemCols);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if (warp < kGfProducerWarps) {
+  if (warp < NPW) {
     // =========================== producers ===========================
     uint32_t stage = 0, phase = 0;
-    for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
-      const GramUnit w = gram_decode_unit(p, u);
-      const int nblk = (w.I == w.J) ? 1 : 2;
-      for (int kb = w.kb0; kb < w.kb1; ++kb) {
-        for (int h = 0; h < nblk; ++h) {
-          mbar_wait(bar_empty + 8 * stage, phase ^ 1u, 100u + stage);
-          const uint32_t st_smem = smem_base + stage * kGfStageBytes;
-          const int blk = h == 0 ? w.I : w.J;
-          if (SRC == 0) gram_fill_stage_f32_vec(p, w.b, blk, kb, st_smem, threadIdx.x);
-          else if (SRC == 1) gram_fill_stage_f32_scalar(p, w.b, blk, kb, st_smem, threadIdx.x);
-          else if (SRC == 2) gram_fill_stage_bf16_vec(p, w.b, blk, kb, st_smem, threadIdx.x);
-          else gram_fill_stage_bf16_scalar(p, w.b, blk, kb, st_smem, threadIdx.x);
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_full + 8 * stage);
-          if (++stage == kGfStages) { stage = 0; phase ^= 1u; }
-        }
-      }
-    }
-  } else if (warp == kGfMmaWarp) {
-    // =========================== MMA issuer ===========================
-    uint32_t stage = 0, phase = 0, acc_phase = 0;
-    const uint32_t idesc256 = make_idesc_bf16(128, 256), idesc128 = make_idesc_bf16(128, 128);
-    for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
-      const GramUnit w = gram_decode_unit(p, u);
-      const bool diag = (w.I == w.J);
-      mbar_wait(bar_tempty, acc_phase ^ 1u, 200u);   // epilogue has drained the previous unit's accumulators
-      tc_fence_after_sync();
-      for (int kb = w.kb0; kb < w.kb1; ++kb) {
-        const uint32_t sA = stage;
-        mbar_wait(bar_full + 8 * sA, phase, 300u + sA);
-        uint32_t sB = sA, phaseB = phase;
-        if (!diag) {
-          sB = sA + 1;
-          if (sB == kGfStages) { sB = 0; phaseB ^= 1u; }
-          mbar_wait(bar_full + 8 * sB, phaseB, 310u + sB);
-        }
-        tc_fence_after_sync();
-        if (lane == 0) {
-          const uint32_t aI = smem_base + sA * kGfStageBytes;   // rows of block I
-          const uint32_t aJ = smem_base + sB * kGfStageBytes;   // rows of block J (== I on the diagonal)
-          const uint32_t acc = (kb > w.kb0) ? 1u : 0u;
-#pragma unroll
-          for (uint32_t ks = 0; ks < kTileK / kUmmaK; ++ks) {
-            const uint32_t koff = ks * 32u;
-            // acc0: I rows 0-127 x J rows 0-255
-            umma_bf16(tmem_base + 0u, make_smem_desc_sw128(aI + koff), make_smem_desc_sw128(aJ + koff), idesc256,
-                      acc | ks);
-            if (diag) {
-              // acc1: I rows 128-255 x I rows 128-255 (the lower-left 128x128 block is never computed)
-              umma_bf16(tmem_base + 256u, make_smem_desc_sw128(aI + 128u * kRowBytes + koff),
-                        make_smem_desc_sw128(aI + 128u * kRowBytes + koff), idesc128, acc | ks);
-            } else {
-              // acc1: I rows 128-255 x J rows 0-255
-              umma_bf16(tmem_base + 256u, make_smem_desc_sw128(aI + 128u * kRowBytes + koff),
-                        make_smem_desc_sw128(aJ + koff), idesc256, acc | ks);
-            }
-          }
-          umma_commit(bar_empty + 8 * sA);
-          if (!diag) umma_commit(bar_empty + 8 * sB);
-          if (kb + 1 == w.kb1) umma_commit(bar_tfull);
-        }
-        __syncwarp();
-        stage = sB + 1; phase = phaseB;
-        if (stage == kGfStages) { stage = 0; phase ^= 1u; }
-      }
-      acc_phase ^= 1u;
+    const int tid = threadIdx.x;
+    GfRegs<SRC, 4096 / NT> ra, rb;
+    GfItem cur;
+    bool have = gf_item_first(cur, p);
+    if (have) gf_load<SRC, NT>(p, cur, ra, tid);
+    while (have) {
+      GfItem n1 = cur;
+      const bool h1 = gf_item_next(n1, p);
+      if (h1) gf_load<SRC, NT>(p, n1, rb, tid);    // next stage's loads fly while this one is stored
+      gf_publish<SRC, NT>(p, cur, ra, smem_base, bar_full, bar_empty, stage, phase, tid, lane);
+      if (!h1) break;
+      cur = n1;
+      have = gf_item_next(cur, p);
+      if (have) gf_load<SRC, NT>(p, cur, ra, tid);
+      gf_publish<SRC, NT>(p, n1, rb, smem_base, bar_full, bar_empty, stage, phase, tid, lane);
     }
   } else {
-    // =========================== epilogue ===========================
-    const int q = warp - kGfEpiWarp0;   // TMEM lane quarter this warp may read (= warp % 4)
+    // =========================== MMA issue (first warp) + epilogue (all four) ===========================
+    const int q = warp - kEpiWarp0;   // TMEM lane quarter this warp may read (= warp % 4)
     uint32_t acc_phase = 0;
+    uint32_t stage = 0, phase = 0;
+    const uint32_t idesc256 = make_idesc_bf16(128, 256), idesc128 = make_idesc_bf16(128, 128);
+    const bool atomics = p.use_atomics != 0;
     for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
       const GramUnit w = gram_decode_unit(p, u);
       const bool diag = (w.I == w.J);
+      if (q == 0) {
+        mbar_wait(bar_tempty, acc_phase ^ 1u, 200u);   // all four warps have drained the previous unit's accumulators
+        tc_fence_after_sync();
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
+          const uint32_t sA = stage;
+          mbar_wait(bar_full + 8 * sA, phase, 300u + sA);
+          uint32_t sB = sA, phaseB = phase;
+          if (!diag) {
+            sB = sA + 1;
+            if (sB == kGfStages) { sB = 0; phaseB ^= 1u; }
+            mbar_wait(bar_full + 8 * sB, phaseB, 310u + sB);
+          }
+          tc_fence_after_sync();
+          if (lane == 0) {
+            const uint32_t aI = smem_base + sA * kGfStageBytes;   // rows of block I
+            const uint32_t aJ = smem_base + sB * kGfStageBytes;   // rows of block J (== I on the diagonal)
+            const uint32_t acc = (kb > w.kb0) ? 1u : 0u;
+#pragma unroll
+            for (uint32_t ks = 0; ks < kTileK / kUmmaK; ++ks) {
+              if ((int)(kb * 64 + ks * 16) >= p.HW) break;        // K tail: whole k-steps past HW are skipped
+              const uint32_t koff = ks * 32u;
+              // acc0: I rows 0-127 x J rows 0-255
+              umma_bf16(tmem_base + 0u, make_smem_desc_sw128(aI + koff), make_smem_desc_sw128(aJ + koff), idesc256,
+                        acc | ks);
+              if (diag) {
+                // acc1: I rows 128-255 x I rows 128-255 (the lower-left 128x128 block is never computed)
+                umma_bf16(tmem_base + 256u, make_smem_desc_sw128(aI + 128u * kRowBytes + koff),
+                          make_smem_desc_sw128(aI + 128u * kRowBytes + koff), idesc128, acc | ks);
+              } else {
+                // acc1: I rows 128-255 x J rows 0-255
+                umma_bf16(tmem_base + 256u, make_smem_desc_sw128(aI + 128u * kRowBytes + koff),
+                          make_smem_desc_sw128(aJ + koff), idesc256, acc | ks);
+              }
+            }
+            umma_commit(bar_empty + 8 * sA);
+            if (!diag) umma_commit(bar_empty + 8 * sB);
+            if (kb + 1 == w.kb1) umma_commit(bar_tfull);
+          }
+          __syncwarp();
+          stage = sB + 1; phase = phaseB;
+          if (stage == kGfStages) { stage = 0; phase ^= 1u; }
+        }
+      }
       mbar_wait(bar_tfull, acc_phase, 400u);
       tc_fence_after_sync();
       float* outp = p.out + (long long)w.b * p.out_img_stride;
@@ -340,15 +379,18 @@ __global__ void __launch_bounds__(kGfThreads, 1) gram_fwd_kernel(const GramFwdPa
         const int c_row = w.I * 256 + a * 128 + q * 32 + lane;
         const int ncols = (a == 1 && diag) ? 128 : 256;
         const int colbase = w.J * 256 + ((a == 1 && diag) ? 128 : 0);
+        if (w.I * 256 + a * 128 >= p.C) break;   // whole accumulator is padding (C <= 128)
 #pragma unroll 1
         for (int n0 = 0; n0 < ncols; n0 += 32) {
+          const int c_col0 = colbase + n0;
+          if (c_col0 >= p.C) break;              // padding columns
           float v[32];
           tmem_ld32(lane_addr + (uint32_t)(a * 256 + n0), v);
-          const int c_col0 = colbase + n0;
           // a 128x128 block strictly above the diagonal is mirrored; diagonal blocks are complete on their own
           const bool mirror = (c_col0 >> 7) > (c_row >> 7);
-          if (KP > 0) gram_epi_pool_chunk<(KP > 0 ? KP : 1)>(v, c_row, c_col0, p.C, p.g, p.scale, outp, mirror, lane);
-          else gram_epi_dense_chunk(v, c_row, c_col0, p.C, p.scale, outp, mirror, p.use_atomics != 0);
+          if (KP > 0)
+            gram_epi_pool_chunk<(KP > 0 ? KP : 1)>(v, c_row, c_col0, p.C, p.g, p.scale, outp, mirror, atomics, lane);
+          else gram_epi_dense_chunk(v, c_row, c_col0, p.C, p.scale, outp, mirror, atomics);
         }
       }
       tc_fence_before_sync();
@@ -360,7 +402,7 @@ __global__ void __launch_bounds__(kGfThreads, 1) gram_fwd_kernel(const GramFwdPa
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == kGfMmaWarp) {
+  if (warp == kMmaWarp) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, kGfTmemCols);
   }

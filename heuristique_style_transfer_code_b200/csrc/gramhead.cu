@@ -5,6 +5,7 @@
 #include "gram_fwd.cuh"
 #include "gram_bwd.cuh"
 #include "attn_head.cuh"
+#include <string>
 
 namespace gh {
 
@@ -41,15 +42,24 @@ static int choose_ksplit(long long base_units, int nkb, int ctas) {
   return best;
 }
 
+// Tuning knobs (gh_set_option)
+static int g_opt_fwd_producer_warps = 16;
+
+template <int SRC, int KP, int NPW>
+static cudaError_t launch_gram_fwd_one(const GramFwdParams& p, int grid, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(gram_fwd_kernel<SRC, KP, NPW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)kGfSmemBytes);
+  if (e != cudaSuccess) return e;
+  gram_fwd_kernel<SRC, KP, NPW><<<grid, (NPW + 4) * 32, kGfSmemBytes, st>>>(p);
+  return cudaGetLastError();
+}
+
 template <int SRC>
 static cudaError_t launch_gram_fwd_kp(const GramFwdParams& p, int kp, int grid, cudaStream_t st) {
-#define GH_LAUNCH_GF(KP)                                                                                        \
-  {                                                                                                             \
-    cudaError_t e = cudaFuncSetAttribute(gram_fwd_kernel<SRC, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                         (int)kGfSmemBytes);                                                    \
-    if (e != cudaSuccess) return e;                                                                             \
-    gram_fwd_kernel<SRC, KP><<<grid, kGfThreads, kGfSmemBytes, st>>>(p);                                        \
-    return cudaGetLastError();                                                                                  \
+#define GH_LAUNCH_GF(KP)                                                                  \
+  {                                                                                       \
+    if (g_opt_fwd_producer_warps == 8) return launch_gram_fwd_one<SRC, KP, 8>(p, grid, st); \
+    return launch_gram_fwd_one<SRC, KP, 16>(p, grid, st);                                 \
   }
   switch (kp) {
     case 0: GH_LAUNCH_GF(0)
@@ -94,12 +104,15 @@ static int gram_fwd_common(const void* F, int f_dtype, long long img_stride, lon
   p.total_units = (int)total;
   p.g = g; p.out = out; p.out_img_stride = out_img_stride;
   p.scale = (mode == GRAM_POOL) ? 1.0f / ((float)HW * (float)kp * (float)kp) : 1.0f / (float)HW;
-  p.use_atomics = (ksplit > 1) ? 1 : 0;
+  // every output element has exactly one writer unless K is split or a pooled row spans two epilogue warps (k > 32)
+  p.use_atomics = (ksplit > 1 || kp > 32) ? 1 : 0;
 
   cudaError_t e;
   if (mode == GRAM_POOL) {
-    e = cudaMemset2DAsync(out, (size_t)out_img_stride * 4, 0, (size_t)g * g * 4, (size_t)B, st);
-    if (e != cudaSuccess) return (int)e;
+    if (p.use_atomics) {
+      e = cudaMemset2DAsync(out, (size_t)out_img_stride * 4, 0, (size_t)g * g * 4, (size_t)B, st);
+      if (e != cudaSuccess) return (int)e;
+    }
   } else if (p.use_atomics) {
     e = cudaMemsetAsync(out, 0, (size_t)B * C * C * 4, st);
     if (e != cudaSuccess) return (int)e;
@@ -222,6 +235,17 @@ extern "C" {
 int gh_version(void) { return 100; }
 
 int gh_sm_count(void) { return sm_count_cached(); }
+
+int gh_set_option(const char* name, int value) {
+  if (!name) return GH_ERR_BAD_ARG;
+  const std::string key(name);
+  if (key == "gram_fwd_producer_warps") {
+    if (value != 8 && value != 16) return GH_ERR_BAD_ARG;
+    g_opt_fwd_producer_warps = value;
+    return 0;
+  }
+  return GH_ERR_BAD_ARG;
+}
 
 int gh_last_device_error(unsigned int* out4) {
   if (!out4) return GH_ERR_BAD_ARG;

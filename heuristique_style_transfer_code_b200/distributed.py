@@ -1,0 +1,102 @@
+"""One process per GPU, batch-sharded (images are independent units of this path).
+
+The reference is single-process (no torch.distributed anywhere); this is the harness the multi-GPU configurations of
+BASELINE.json need around its loops:
+  * inference / evaluation: each rank runs the model on its contiguous batch shard; the only collective is the gather
+    of logits (B x nc) and embeddings (B x g*g) for the classification / t-SNE modes -- all_gather_into_tensor;
+  * training: DistributedDataParallel over NCCL (NVLink 5 / NVSwitch) averages the 12.7 M fp32 gradients (51 MB per
+    step at truncate_layer 7); the head's gradients are produced first in backward, the encoder's last, so DDP's
+    buckets overlap the all-reduce with the cuDNN backward of the encoder.
+BatchNorm note: the reference trains with plain BatchNorm in train mode; under data parallelism each rank normalises
+with its own shard's statistics (standard DDP behaviour) unless `sync_bn=True` converts the encoder to SyncBatchNorm.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int, torch.device]:
+    """Reads RANK / WORLD_SIZE / LOCAL_RANK / MASTER_* (torchrun). Single-process when WORLD_SIZE is absent or 1."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    use_cuda = torch.cuda.is_available()
+    device = torch.device(f"cuda:{local}") if use_cuda else torch.device("cpu")
+    if use_cuda:
+        torch.cuda.set_device(device)
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        kwargs = {}
+        if use_cuda:
+            kwargs["device_id"] = device
+        dist.init_process_group(backend or ("nccl" if use_cuda else "gloo"), rank=rank, world_size=world, **kwargs)
+    return rank, world, local, device
+
+
+def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous shard [lo, hi) of n items for `rank`; the first n % world ranks get one extra item."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_batch(x: torch.Tensor, rank: int, world: int) -> torch.Tensor:
+    lo, hi = shard_bounds(x.shape[0], rank, world)
+    return x[lo:hi]
+
+
+def gather_rows(t: torch.Tensor, total_rows: int, world: int) -> torch.Tensor:
+    """Concatenates every rank's rows (dim 0) in rank order. Shards may differ by one row (shard_bounds); they are
+    padded to the largest shard for all_gather_into_tensor and trimmed afterwards."""
+    if world == 1:
+        return t
+    rank = dist.get_rank()
+    longest = shard_bounds(total_rows, 0, world)[1]
+    pad = longest - t.shape[0]
+    src = t.contiguous()
+    if pad:
+        src = torch.cat([src, src.new_zeros((pad,) + tuple(t.shape[1:]))], dim=0)
+    out = src.new_empty((world * longest,) + tuple(t.shape[1:]))
+    dist.all_gather_into_tensor(out, src)
+    if total_rows == world * longest:
+        return out
+    pieces = []
+    for r in range(world):
+        lo, hi = shard_bounds(total_rows, r, world)
+        pieces.append(out[r * longest: r * longest + (hi - lo)])
+    del rank
+    return torch.cat(pieces, dim=0)
+
+
+def wrap_ddp(model: torch.nn.Module, device: torch.device, sync_bn: bool = False, bucket_cap_mb: int = 25,
+             broadcast_buffers: bool = True) -> torch.nn.Module:
+    """DistributedDataParallel around the drop-in model (construct it with device=f'cuda:{local_rank}')."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return model
+    if sync_bn:
+        model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
+    ids = [device.index] if device.type == "cuda" else None
+    return torch.nn.parallel.DistributedDataParallel(model, device_ids=ids, bucket_cap_mb=bucket_cap_mb,
+                                                     broadcast_buffers=broadcast_buffers,
+                                                     gradient_as_bucket_view=True)
+
+
+def max_over_ranks(value: float, device: torch.device) -> float:
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(device: torch.device) -> None:
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        if device.type == "cuda":
+            dist.barrier(device_ids=[device.index])
+        else:
+            dist.barrier()

@@ -16,6 +16,31 @@ from ._lib import GH_DTYPE_BF16, GH_DTYPE_F32, GramHeadError, check
 KSPLIT = 0
 MAX_CTAS = 0
 
+# Accounting used by bench.py: number of kernels of this library launched, and (when PROFILE is a list) one
+# (name, work dict, start event, end event) record per C-ABI call, timed on the stream the call is enqueued on.
+LAUNCHES = 0
+PROFILE = None
+
+
+class _Timed:
+    def __init__(self, name, kernels, device, **work):
+        self.name, self.kernels, self.device, self.work = name, kernels, device, work
+
+    def __enter__(self):
+        global LAUNCHES
+        LAUNCHES += self.kernels
+        if PROFILE is not None:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.end = torch.cuda.Event(enable_timing=True)
+            self.start.record(torch.cuda.current_stream(self.device))
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None and exc[0] is None:
+            self.end.record(torch.cuda.current_stream(self.device))
+            PROFILE.append((self.name, self.work, self.start, self.end))
+        return False
+
 
 def _stream_ptr(t: torch.Tensor) -> int:
     return torch.cuda.current_stream(t.device).cuda_stream
@@ -65,7 +90,8 @@ def gram_pool_fwd_(x: torch.Tensor, g: int, desc: torch.Tensor, l: int) -> None:
     """desc[:, l, :] = vec(pool_g(F F^T / HW)) for stage activation x. desc: (B, L, g*g) fp32 contiguous."""
     x, code, s_img, s_row, b, c, hw = _feature_view(x)
     assert desc.is_contiguous() and desc.dtype == torch.float32 and desc.shape[0] == b and desc.shape[2] == g * g
-    with torch.cuda.device(x.device):
+    work = dict(bytes=b * c * hw * x.element_size() + b * g * g * 4, flops=b * c * (c + 1) * hw, kind="gram_fwd")
+    with torch.cuda.device(x.device), _Timed(f"gram_pool_fwd[C={c},HW={hw},{x.dtype}]", 1, x.device, **work):
         rc = _lib.lib().gh_gram_pool_fwd(x.data_ptr(), code, s_img, s_row, b, c, hw, g, desc.data_ptr(), l,
                                          desc.shape[1], KSPLIT, MAX_CTAS, _stream_ptr(x))
     check(rc, "gh_gram_pool_fwd")
@@ -74,7 +100,8 @@ def gram_pool_fwd_(x: torch.Tensor, g: int, desc: torch.Tensor, l: int) -> None:
 def gram_dense_fwd(x: torch.Tensor) -> torch.Tensor:
     x, code, s_img, s_row, b, c, hw = _feature_view(x)
     out = torch.empty((b, c, c), device=x.device, dtype=torch.float32)
-    with torch.cuda.device(x.device):
+    work = dict(bytes=b * c * hw * x.element_size() + b * c * c * 4, flops=b * c * (c + 1) * hw, kind="gram_fwd")
+    with torch.cuda.device(x.device), _Timed(f"gram_dense_fwd[C={c},HW={hw},{x.dtype}]", 1, x.device, **work):
         rc = _lib.lib().gh_gram_dense_fwd(x.data_ptr(), code, s_img, s_row, b, c, hw, out.data_ptr(), KSPLIT, MAX_CTAS,
                                           _stream_ptr(x))
     check(rc, "gh_gram_dense_fwd")
@@ -85,7 +112,8 @@ def gram_pool_bwd(x: torch.Tensor, g: int, d_desc: torch.Tensor, l: int) -> torc
     x, code, s_img, s_row, b, c, hw = _feature_view(x)
     d_desc = d_desc.contiguous()
     df = torch.empty((b, c, hw), device=x.device, dtype=torch.float32)
-    with torch.cuda.device(x.device):
+    work = dict(bytes=b * c * hw * (x.element_size() + 4) + b * g * g * 4, flops=2 * b * c * c * hw, kind="gram_bwd")
+    with torch.cuda.device(x.device), _Timed(f"gram_pool_bwd[C={c},HW={hw},{x.dtype}]", 1, x.device, **work):
         rc = _lib.lib().gh_gram_pool_bwd(x.data_ptr(), code, s_img, s_row, b, c, hw, g, d_desc.data_ptr(), l,
                                          d_desc.shape[1], df.data_ptr(), c * hw, hw, MAX_CTAS, _stream_ptr(x))
     check(rc, "gh_gram_pool_bwd")
@@ -96,7 +124,8 @@ def gram_dense_bwd(x: torch.Tensor, d_gram: torch.Tensor) -> torch.Tensor:
     x, code, s_img, s_row, b, c, hw = _feature_view(x)
     d_gram = d_gram.contiguous().float()
     df = torch.empty((b, c, hw), device=x.device, dtype=torch.float32)
-    with torch.cuda.device(x.device):
+    work = dict(bytes=b * c * hw * (x.element_size() + 4) + b * c * c * 4, flops=2 * b * c * c * hw, kind="gram_bwd")
+    with torch.cuda.device(x.device), _Timed(f"gram_dense_bwd[C={c},HW={hw},{x.dtype}]", 1, x.device, **work):
         rc = _lib.lib().gh_gram_dense_bwd(x.data_ptr(), code, s_img, s_row, b, c, hw, d_gram.data_ptr(), df.data_ptr(),
                                           c * hw, hw, MAX_CTAS, _stream_ptr(x))
     check(rc, "gh_gram_dense_bwd")
@@ -105,7 +134,7 @@ def gram_dense_bwd(x: torch.Tensor, d_gram: torch.Tensor) -> torch.Tensor:
 
 def adaptive_pool_fwd_(gram: torch.Tensor, g: int, desc: torch.Tensor, l: int) -> None:
     b, c, _ = gram.shape
-    with torch.cuda.device(gram.device):
+    with torch.cuda.device(gram.device), _Timed("adaptive_pool_fwd", 1, gram.device, bytes=b * c * c * 4, flops=0, kind="pool"):
         rc = _lib.lib().gh_adaptive_pool_fwd(gram.data_ptr(), b, c, g, desc.data_ptr(), l, desc.shape[1],
                                              _stream_ptr(gram))
     check(rc, "gh_adaptive_pool_fwd")
@@ -115,7 +144,7 @@ def adaptive_pool_bwd(d_desc: torch.Tensor, l: int, c: int, g: int) -> torch.Ten
     d_desc = d_desc.contiguous()
     b = d_desc.shape[0]
     dg = torch.empty((b, c, c), device=d_desc.device, dtype=torch.float32)
-    with torch.cuda.device(d_desc.device):
+    with torch.cuda.device(d_desc.device), _Timed("adaptive_pool_bwd", 1, d_desc.device, bytes=b * c * c * 4, flops=0, kind="pool"):
         rc = _lib.lib().gh_adaptive_pool_bwd(d_desc.data_ptr(), l, d_desc.shape[1], b, c, g, dg.data_ptr(),
                                              _stream_ptr(d_desc))
     check(rc, "gh_adaptive_pool_bwd")
@@ -199,7 +228,9 @@ class _AttnHead(torch.autograd.Function):
         obar = torch.empty((b, e), device=dev, dtype=torch.float32)
         emb = torch.empty((b, e), device=dev, dtype=torch.float32)
         logits = torch.empty((b, nc), device=dev, dtype=torch.float32)
-        with torch.cuda.device(dev):
+        work = dict(bytes=(3 * e * e + e * e + nc * e) * 4 + b * L * e * 4 * 5, kind="attn",
+                    flops=2 * b * L * e * 3 * e + 2 * b * e * e + 2 * b * e * nc + 4 * b * L * L * e)
+        with torch.cuda.device(dev), _Timed(f"attn_head_fwd[B={b},L={L},E={e}]", 4, dev, **work):
             rc = _lib.lib().gh_attn_head_fwd(desc.data_ptr(), *[p.data_ptr() for p in ps], b, L, e, nc, qkv.data_ptr(),
                                              probs.data_ptr(), obar.data_ptr(), emb.data_ptr(), logits.data_ptr(),
                                              _stream_ptr(desc))
@@ -227,7 +258,9 @@ class _AttnHead(torch.autograd.Function):
         lib = _lib.lib()
         ws = torch.empty((lib.gh_attn_head_bwd_workspace(b, L, e),), device=dev, dtype=torch.float32)
         ptr = lambda t: 0 if t is None else t.data_ptr()
-        with torch.cuda.device(dev):
+        work = dict(bytes=(3 * e * e + e * e + nc * e) * 4 * 2 + b * L * e * 4 * 8, kind="attn",
+                    flops=2 * (2 * b * L * e * 3 * e + 2 * b * e * e + 2 * b * e * nc) + 8 * b * L * L * e)
+        with torch.cuda.device(dev), _Timed(f"attn_head_bwd[B={b},L={L},E={e}]", 10, dev, **work):
             rc = lib.gh_attn_head_bwd(desc.data_ptr(), w_in.data_ptr(), w_out.data_ptr(), w_c.data_ptr(), qkv.data_ptr(),
                                       probs.data_ptr(), obar.data_ptr(), emb.data_ptr(), d_logits.data_ptr(), ptr(d_emb),
                                       b, L, e, nc, ptr(d_desc), ptr(gw_in), ptr(gb_in), ptr(gw_out), ptr(gb_out),

@@ -32,6 +32,10 @@ int gh_version(void);
 /* Number of SMs the launchers size their persistent grids by (cudaDevAttrMultiProcessorCount of the current device). */
 int gh_sm_count(void);
 
+/* Launch tuning, process-wide. Known names: "gram_fwd_producer_warps" (8 or 16, default 16). Unknown name or value
+ * outside the allowed set: GH_ERR_BAD_ARG. */
+int gh_set_option(const char* name, int value);
+
 /* Copies the device-side error record {code, blockIdx.x, threadIdx.x, site} to host memory `out4` and clears it.
  * code 1 = an mbarrier wait inside a kernel ran out of time (the kernel traps instead of hanging). Synchronises. */
 int gh_last_device_error(unsigned int* out4);

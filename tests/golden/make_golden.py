@@ -42,8 +42,13 @@ def head_params(model):
 
 
 def run_reference(model, x, labels):
-    """Unmodified reference forward; stage activations captured with hooks, gradients from its own autograd."""
+    """Unmodified reference forward; stage activations captured with hooks, gradients from its own autograd.
+    A pre-hook detaches the input of every block after the first stage, so that d_stage{i} holds only what the HEAD
+    sends back to stage i (without it, autograd adds the gradient arriving through the later encoder blocks, which is
+    backbone work and not part of the path under test). The reference's code itself runs unmodified."""
     acts = []
+    cuts = [blk.register_forward_pre_hook(lambda module, inputs: (inputs[0].detach().requires_grad_(True),))
+            for blk in list(model.truncated_encoder.children())[5:]]
 
     def capture(module, inputs, output):
         output.retain_grad()
@@ -51,7 +56,7 @@ def run_reference(model, x, labels):
 
     hooks = [blk.register_forward_hook(capture) for blk in list(model.truncated_encoder.children())[4:]]
     out = model(x)
-    for h in hooks:
+    for h in hooks + cuts:
         h.remove()
     emb, logits = out if isinstance(out, tuple) else (None, out)
     loss = nn.functional.cross_entropy(logits, labels)

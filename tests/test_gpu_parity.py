@@ -1,0 +1,240 @@
+"""Parity of the sm_100a kernels against the oracle, through the C ABI (ops.py is a thin ctypes layer over it).
+
+Tolerances (written next to each assert):
+  * Gram / descriptor vs the fp64 oracle on fp32 inputs:            normwise rel. err <= 1e-3  (task statement; bf16
+    operands, fp32 accumulation) -- measured 2e-5 .. 3e-4
+  * same vs the fp64 oracle fed bf16-rounded operands:               <= 1e-5  (only fp32 accumulation order differs)
+  * attention head fwd/bwd (fp32 FMA kernels) vs fp64 oracle:        <= 2e-5
+  * Gram backward (bf16 operands incl. the bf16-rounded gradient):   <= 6e-3 normwise
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import head_params_from
+from oracle import head_fp64 as O
+
+pytestmark = pytest.mark.gpu
+
+STAGES = ("stage0", "stage1", "stage2")
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from heuristique_style_transfer_code_b200 import ops as _ops
+    from heuristique_style_transfer_code_b200 import _lib
+    _lib.lib()          # fails loudly when the .so is missing
+    return _ops
+
+
+def npf(t):
+    return t.detach().float().cpu().numpy()
+
+
+def test_cuda_is_present():
+    assert torch.cuda.is_available(), "pytest -m gpu must run on a CUDA machine"
+    assert torch.cuda.get_device_capability()[0] == 10, "kernels are built for sm_100a only"
+
+
+@pytest.mark.parametrize("B,C,HW,g,ksplit,dtype", [
+    (1, 256, 64, 32, 1, "f32"),            # single K block
+    (2, 256, 3136, 32, 1, "f32"),          # layer1 @224
+    (3, 512, 784, 32, 1, "f32"),           # layer2: 3 super-tiles, off-diagonal one uses two smem stages per k-block
+    (2, 1024, 196, 32, 1, "f32"),          # layer3: K tail 196 = 3*64 + 4
+    (2, 2048, 49, 32, 1, "f32"),           # layer4: unaligned rows -> scalar loader, k = 64 -> atomics
+    (5, 256, 3136, 32, 0, "f32"),          # auto K split
+    (5, 256, 3136, 32, 4, "f32"),          # K split, fp32 atomics
+    (2, 256, 3136, 32, 1, "bf16"),         # bf16 features
+    (2, 256, 12544, 32, 0, "f32"),         # layer1 @448 (camera config)
+    (2, 1024, 196, 8, 1, "f32"),           # k = 128
+    (2, 256, 100, 64, 1, "f32"),           # k = 4
+    (2, 64, 3136, 32, 1, "f32"),           # C < 128: second accumulator is all padding
+    (300, 256, 256, 32, 1, "f32"),         # more units than CTAs: persistent loop, ring wrap
+    (1, 256, 3136, 32, 0, "f32"),          # batch 1 (camera): K split fills the SMs
+])
+def test_pooled_gram_forward(ops, B, C, HW, g, ksplit, dtype):
+    torch.manual_seed(0)
+    x = torch.relu(torch.randn(B, C, HW, device="cuda"))
+    if dtype == "bf16":
+        x = x.bfloat16()
+    desc = torch.full((B, 2, g * g), float("nan"), device="cuda")
+    ops.KSPLIT = ksplit
+    try:
+        ops.gram_pool_fwd_(x, g, desc, 1)
+    finally:
+        ops.KSPLIT = 0
+    torch.cuda.synchronize()
+    got = npf(desc[:, 1])
+    xf = npf(x)
+    assert torch.isnan(desc[:, 0]).all(), "the other stage's slice must not be touched"
+    assert O.rel_err(got, O.descriptors([xf], g)[:, 0]) <= 1e-3
+    assert O.rel_err(got, O.descriptors([xf], g, operand_rounding="bf16")[:, 0]) <= 1e-5
+    sym = got.reshape(B, g, g)
+    assert np.abs(sym - sym.transpose(0, 2, 1)).max() <= 1e-5 * np.abs(sym).max()
+
+
+def test_producer_warp_variants_agree(ops):
+    from heuristique_style_transfer_code_b200 import _lib
+    torch.manual_seed(0)
+    x = torch.relu(torch.randn(4, 512, 784, device="cuda"))
+    outs = []
+    for npw in (8, 16):
+        assert _lib.lib().gh_set_option(b"gram_fwd_producer_warps", npw) == 0
+        desc = torch.empty((4, 1, 1024), device="cuda")
+        ops.KSPLIT = 1
+        ops.gram_pool_fwd_(x, 32, desc, 0)
+        ops.KSPLIT = 0
+        outs.append(desc.clone())
+    _lib.lib().gh_set_option(b"gram_fwd_producer_warps", 16)
+    assert torch.equal(outs[0], outs[1])     # same summation order -> bit identical
+
+
+@pytest.mark.parametrize("B,C,HW,ksplit", [(1, 64, 3136, 1), (2, 256, 784, 1), (2, 512, 196, 1), (1, 64, 3136, 0),
+                                           (2, 320, 100, 1), (1, 256, 49, 1)])
+def test_dense_gram_forward(ops, B, C, HW, ksplit):
+    torch.manual_seed(0)
+    x = torch.relu(torch.randn(B, C, HW, device="cuda"))
+    ops.KSPLIT = ksplit
+    try:
+        G = ops.gram_dense_fwd(x)
+    finally:
+        ops.KSPLIT = 0
+    torch.cuda.synchronize()
+    assert O.rel_err(npf(G), O.gram(npf(x))) <= 1e-3
+    assert O.rel_err(npf(G), O.gram(O.bf16_round(npf(x)))) <= 1e-5
+    assert float((G - G.transpose(1, 2)).abs().max()) <= 1e-6 * float(G.abs().max())
+
+
+@pytest.mark.parametrize("B,C,HW,g,dtype", [(1, 256, 128, 32, "f32"), (2, 256, 3136, 32, "f32"), (2, 512, 784, 32, "f32"),
+                                            (2, 1024, 196, 32, "f32"), (2, 2048, 49, 32, "f32"),
+                                            (2, 256, 3136, 32, "bf16"), (40, 256, 784, 32, "f32"), (2, 64, 100, 16, "f32")])
+def test_pooled_gram_backward(ops, B, C, HW, g, dtype):
+    torch.manual_seed(0)
+    x = torch.relu(torch.randn(B, C, HW, device="cuda"))
+    if dtype == "bf16":
+        x = x.bfloat16()
+    dd = torch.randn(B, 2, g * g, device="cuda")
+    df = ops.gram_pool_bwd(x, g, dd, 1)
+    torch.cuda.synchronize()
+    assert O.rel_err(npf(df), O.gram_pool_backward(npf(x), g, npf(dd[:, 1]))) <= 6e-3
+
+
+@pytest.mark.parametrize("B,C,HW", [(1, 64, 3136), (2, 256, 196), (1, 512, 100)])
+def test_dense_gram_backward(ops, B, C, HW):
+    torch.manual_seed(0)
+    x = torch.relu(torch.randn(B, C, HW, device="cuda"))
+    dg = torch.randn(B, C, C, device="cuda")
+    df = ops.gram_dense_bwd(x, dg)
+    torch.cuda.synchronize()
+    assert O.rel_err(npf(df), O.gram_dense_backward(npf(x), npf(dg))) <= 6e-3
+
+
+@pytest.mark.parametrize("B,C,HW,g", [(2, 256, 196, 24), (2, 64, 100, 7)])
+def test_general_bins_path(ops, B, C, HW, g):
+    """C % g != 0: torch's overlapping bins -> dense Gram kernel + bin-rule pooling kernels (forward and backward)."""
+    torch.manual_seed(0)
+    x = torch.relu(torch.randn(B, C, HW, device="cuda")).requires_grad_(True)
+    desc = ops.style_descriptor([x], g)
+    w = torch.randn_like(desc)
+    (desc * w).sum().backward()
+    torch.cuda.synchronize()
+    assert O.rel_err(npf(desc), O.descriptors([npf(x)], g)) <= 1e-3
+    assert O.rel_err(npf(x.grad), O.gram_pool_backward(npf(x), g, npf(w[:, 0]))) <= 6e-3
+
+
+@pytest.mark.parametrize("B,L,g,nc", [(5, 3, 8, 4), (33, 3, 32, 4), (4, 1, 16, 3), (7, 4, 8, 10), (1, 3, 32, 4)])
+def test_attention_head_forward_backward(ops, B, L, g, nc):
+    E = g * g
+    torch.manual_seed(0)
+    desc = torch.randn(B, L, E, device="cuda") * 2.0
+    mha = torch.nn.MultiheadAttention(E, 1).cuda()
+    lin = torch.nn.Linear(E, nc).cuda()
+    with torch.no_grad():
+        mha.in_proj_bias.normal_(0, 0.1)
+        mha.out_proj.bias.normal_(0, 0.1)
+    ps = [mha.in_proj_weight, mha.in_proj_bias, mha.out_proj.weight, mha.out_proj.bias, lin.weight, lin.bias]
+    d = desc.clone().requires_grad_(True)
+    emb, logits = ops.attention_head(d, *ps)
+    labels = torch.arange(B, device="cuda") % nc
+    w = torch.randn(B, E, device="cuda") * 0.01
+    (torch.nn.functional.cross_entropy(logits, labels) + (emb * w).sum()).backward()
+    torch.cuda.synchronize()
+    names = ("in_proj_weight", "in_proj_bias", "out_proj_weight", "out_proj_bias", "classifier_weight", "classifier_bias")
+    params = {k: npf(p) for k, p in zip(names, ps)}
+    c = O.attention_forward(npf(desc), *[params[k] for k in names])
+    _, dl = O.cross_entropy(c["logits"], labels.cpu().numpy())
+    gr = O.attention_backward(c, params, dl, npf(w))
+    assert O.rel_err(npf(emb), c["emb"]) <= 2e-5
+    assert O.rel_err(npf(logits), c["logits"]) <= 2e-5
+    assert O.rel_err(npf(d.grad), gr["d_desc"]) <= 2e-5
+    for k, p in zip(names, ps):
+        assert O.rel_err(npf(p.grad), gr[k]) <= 2e-5, k
+
+
+def test_golden_small_head_forward_backward(ops, golden_small):
+    """Fixture produced by the unmodified reference (tests/golden/make_golden.py): k = 8/16/32 at g = 8."""
+    d = golden_small
+    g = int(d["g"])
+    feats = [torch.from_numpy(d[s]).cuda().requires_grad_(True) for s in STAGES]
+    ps = [torch.from_numpy(v).cuda().requires_grad_(True) for v in head_params_from(d).values()]
+    desc = ops.style_descriptor(feats, g)
+    emb, logits = ops.attention_head(desc, *ps)
+    loss = torch.nn.functional.cross_entropy(logits, torch.from_numpy(d["labels"]).cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    assert O.rel_err(npf(emb), d["embeddings"]) <= 1e-3
+    assert O.rel_err(npf(logits), d["logits"]) <= 1e-3
+    assert np.array_equal(npf(logits).argmax(1), d["logits"].argmax(1))
+    assert abs(loss.item() - float(d["loss"])) <= 1e-3 * abs(float(d["loss"]))
+    for f, s in zip(feats, STAGES):
+        assert O.rel_err(npf(f.grad), d["d_" + s]) <= 6e-3, s
+    for p, k in zip(ps, head_params_from(d)):
+        assert O.rel_err(npf(p.grad), d["grad_" + k]) <= 2e-3, k
+
+
+def test_golden_resnet_descriptors(ops, golden_resnet):
+    d = golden_resnet
+    feats = [torch.from_numpy(d[s]).cuda() for s in STAGES]
+    desc = ops.style_descriptor(feats, int(d["g"]))
+    torch.cuda.synchronize()
+    assert O.rel_err(npf(desc), d["descriptors"]) <= 1e-3     # bf16-in / fp32-acc vs the fp32 reference
+
+
+# ---- size-independent properties at BASELINE.json's full sizes -------------------------------------------------------
+@pytest.mark.parametrize("C,HW", [(256, 3136), (512, 784), (1024, 196)])
+def test_full_size_properties(ops, C, HW):
+    B, g = 256, 32
+    torch.manual_seed(0)
+    x = torch.relu(torch.randn(B, C, HW, device="cuda"))
+    desc = torch.empty((B, 1, g * g), device="cuda")
+    ops.KSPLIT = 1
+    ops.gram_pool_fwd_(x, g, desc, 0)
+    base = desc.clone()
+    # (1) images are independent: any batch shard gives the same rows, bit for bit (what multi-GPU sharding relies on)
+    part = torch.empty((64, 1, g * g), device="cuda")
+    ops.gram_pool_fwd_(x[128:192], g, part, 0)
+    assert torch.equal(part, base[128:192])
+    # (2) degree-2 homogeneity: scaling by a power of two is exact in bf16 and fp32
+    ops.gram_pool_fwd_(x * 2.0, g, desc, 0)
+    assert torch.equal(desc, base * 4.0)
+    # (3) invariance under a permutation of the spatial positions, up to fp32 summation order
+    perm = torch.randperm(HW, device="cuda")
+    ops.gram_pool_fwd_(x[:, :, perm].contiguous(), g, desc, 0)
+    assert float((desc - base).norm() / base.norm()) <= 1e-5
+    # (4) trace identity: sum of the pooled diagonal * k  ==  mean_c of ||F_c||^2 / HW  summed ... checked in fp64 on a slice
+    k = C // g
+    xs = x[:8].bfloat16().double()
+    tr = (xs * xs).sum(dim=(1, 2)) / HW
+    diag_blocks = base[:8, 0].double().view(8, g, g)
+    # sum over all pooled entries * k^2 = sum_cd G[c][d] = ||sum_c F_c||^2 / HW
+    tot = (xs.sum(dim=1) ** 2).sum(dim=1) / HW
+    assert torch.allclose(diag_blocks.sum(dim=(1, 2)) * k * k, tot, rtol=1e-5)
+    assert (diag_blocks.diagonal(dim1=1, dim2=2).sum(1) * k * k <= tr * k * 1.0001 + 1e-6).all()
+    ops.KSPLIT = 0
+    # (5) K split (atomics) agrees with the deterministic order
+    ops.gram_pool_fwd_(x, g, desc, 0)
+    assert float((desc - base).norm() / base.norm()) <= 1e-5
+    # (6) against torch's fp32 ops on the GPU (the reference's own call sequence) on a 16-image slice
+    xs = x[:16]
+    ref = torch.nn.functional.adaptive_avg_pool2d(torch.bmm(xs, xs.transpose(1, 2)).div(HW), (g, g)).flatten(1)
+    assert float((base[:16, 0] - ref).norm() / ref.norm()) <= 1e-3

@@ -267,12 +267,14 @@ def timing():
     import torch
     from heuristique_style_transfer_code_b200 import ops
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
-    B, g = 256, 32
-    for (C, HW) in [(256, 3136), (512, 784), (1024, 196)]:
+    from heuristique_style_transfer_code_b200 import _lib
+    g = 32
+    for (B, C, HW) in [(256, 256, 3136), (256, 512, 784), (256, 1024, 196), (16, 256, 3136), (1, 256, 12544)]:
         x = torch.relu(torch.randn(B, C, HW, device="cuda"))
         desc = torch.empty(B, 3, g * g, device="cuda")
         dd = torch.randn(B, 3, g * g, device="cuda")
-        for ks in (0, 1, 2, 4, 7):
+        for (npw, ks) in [(16, 0), (16, 1), (16, 4), (8, 0), (8, 1), (8, 4)]:
+            _lib.lib().gh_set_option(b"gram_fwd_producer_warps", npw)
             ops.KSPLIT = ks
             for _ in range(3):
                 ops.gram_pool_fwd_(x, g, desc, 0)
@@ -286,9 +288,10 @@ def timing():
             ms = ev[0].elapsed_time(ev[1]) / n
             by = B * C * HW * 4 + B * g * g * 4
             fl = B * C * (C + 1) * HW
-            print(f"fwd C={C} HW={HW} ksplit={ks}: {ms*1e3:8.1f} us  {by/ms/1e6:8.1f} GB/s ({by/ms/1e6/peaks['hbm_gbs']:.2f} of HBM)"
+            print(f"fwd B={B} C={C} HW={HW} npw={npw} ksplit={ks}: {ms*1e3:8.1f} us  {by/ms/1e6:8.1f} GB/s ({by/ms/1e6/peaks['hbm_gbs']:.2f} of HBM)"
                   f"  {fl/ms/1e9:8.1f} TFLOP/s sym ({fl/ms/1e9/peaks['bf16_tflops']:.2f} of tensor)")
         ops.KSPLIT = 0
+        _lib.lib().gh_set_option(b"gram_fwd_producer_warps", 16)
         for _ in range(3):
             ops.gram_pool_bwd(x, g, dd, 0)
         torch.cuda.synchronize()
@@ -301,7 +304,7 @@ def timing():
         ms = ev[0].elapsed_time(ev[1]) / n
         by = 2 * B * C * HW * 4
         fl = 2 * B * C * C * HW
-        print(f"bwd C={C} HW={HW}: {ms*1e3:8.1f} us  {by/ms/1e6:8.1f} GB/s ({by/ms/1e6/peaks['hbm_gbs']:.2f} of HBM)"
+        print(f"bwd B={B} C={C} HW={HW}: {ms*1e3:8.1f} us  {by/ms/1e6:8.1f} GB/s ({by/ms/1e6/peaks['hbm_gbs']:.2f} of HBM)"
               f"  {fl/ms/1e9:8.1f} TFLOP/s ({fl/ms/1e9/peaks['bf16_tflops']:.2f} of tensor)")
         # torch reference ops on the same GPU (fp32 bmm + div + pool), for scale
         xf = x
