@@ -5,8 +5,10 @@
 // math in SURVEY.md Appendix A):
 //   QKV = X W_in^T + b_in ; S = Q K^T / sqrt(E) per image (L x L, L <= 8) ; A = softmax_keys(S) ; O = A V
 //   Obar = mean_l O[l]    ; emb = Obar W_o^T + b_o  (mean commutes with out_proj) ; logits = emb W_c^T + b_c
-// These GEMMs are ~3 % of the head's FLOPs (the Gram kernels are the other 97 %), and they feed a softmax whose
-// scores reach 1e4-1e5 on a random-init encoder, so they are kept in fp32 FMA rather than bf16 tensor-core math.
+// The linear layers run on tcgen05 with split-bf16 operands (umma_gemm.cuh: fp32-level accuracy, needed because the
+// scores feeding the softmax reach 1e4-1e5 on a random-init encoder); this file holds the per-image attention core,
+// the classifier, the bias-gradient reductions and the fp32 FMA GEMM used for shapes the tensor-core kernel does not
+// take (unaligned E, the nc-wide classifier products).
 #pragma once
 #include "common.cuh"
 
@@ -121,48 +123,86 @@ __device__ __forceinline__ float block_sum_128(float v, float* scratch) {
 }
 
 // One CTA (128 threads) per image. QKV: (B*L, 3E) rows ordered b*L + l. Writes probs (B, L, L) and Obar (B, E).
+// All L*L score dot products are accumulated in one pass over E (each thread keeps L*L partial sums), followed by a
+// single block reduction, instead of L*L separate reductions.
+template <int LT>
 __global__ void __launch_bounds__(128) attn_core_fwd_kernel(const float* __restrict__ QKV, float* __restrict__ probs,
                                                             float* __restrict__ obar, int L, int E) {
-  __shared__ float sc[kMaxL * kMaxL];
-  __shared__ float scratch[4];
+  __shared__ float red[4][LT * LT];
+  __shared__ float sc[LT * LT];
   const int b = blockIdx.x;
   const float* base = QKV + (long long)b * L * 3 * E;
   const float inv_sqrt_e = rsqrtf((float)E);
-  for (int l = 0; l < L; ++l)
-    for (int m = 0; m < L; ++m) {
-      const float* qp = base + (long long)l * 3 * E;
-      const float* kp = base + (long long)m * 3 * E + E;
-      float s = 0.f;
-      for (int e = threadIdx.x; e < E; e += 128) s = fmaf(qp[e] * inv_sqrt_e, kp[e], s);   // torch scales q first
-      s = block_sum_128(s, scratch);
-      if (threadIdx.x == 0) sc[l * kMaxL + m] = s;
+  float acc[LT * LT];
+#pragma unroll
+  for (int i = 0; i < LT * LT; ++i) acc[i] = 0.f;
+  for (int e = threadIdx.x; e < E; e += 128) {
+    float qv[LT], kv[LT];
+#pragma unroll
+    for (int l = 0; l < LT; ++l) {
+      qv[l] = l < L ? base[(long long)l * 3 * E + e] * inv_sqrt_e : 0.f;   // torch scales q before the product
+      kv[l] = l < L ? base[(long long)l * 3 * E + E + e] : 0.f;
     }
+#pragma unroll
+    for (int l = 0; l < LT; ++l)
+#pragma unroll
+      for (int m = 0; m < LT; ++m) acc[l * LT + m] = fmaf(qv[l], kv[m], acc[l * LT + m]);
+  }
+  const int w = threadIdx.x >> 5, ln = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < LT * LT; ++i) {
+    float v = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (ln == 0) red[w][i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < LT * LT) sc[threadIdx.x] = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
   __syncthreads();
   if (threadIdx.x < L) {
     const int l = threadIdx.x;
     float mx = -INFINITY;
-    for (int m = 0; m < L; ++m) mx = fmaxf(mx, sc[l * kMaxL + m]);
+    for (int m = 0; m < L; ++m) mx = fmaxf(mx, sc[l * LT + m]);
     float den = 0.f;
-    for (int m = 0; m < L; ++m) den += expf(sc[l * kMaxL + m] - mx);
+    for (int m = 0; m < L; ++m) den += expf(sc[l * LT + m] - mx);
     for (int m = 0; m < L; ++m) {
-      const float pr = expf(sc[l * kMaxL + m] - mx) / den;
-      sc[l * kMaxL + m] = pr;
+      const float pr = expf(sc[l * LT + m] - mx) / den;
+      sc[l * LT + m] = pr;
       probs[((long long)b * L + l) * L + m] = pr;
     }
   }
   __syncthreads();
   // Obar[e] = (1/L) sum_l sum_m A[l][m] V[m][e] = sum_m (mean_l A[l][m]) V[m][e]
-  float wm[kMaxL];
-  for (int m = 0; m < L; ++m) {
+  float wm[LT];
+#pragma unroll
+  for (int m = 0; m < LT; ++m) {
     float a = 0.f;
-    for (int l = 0; l < L; ++l) a += sc[l * kMaxL + m];
-    wm[m] = a / (float)L;
+    for (int l = 0; l < L; ++l) a += sc[l * LT + m];
+    wm[m] = m < L ? a / (float)L : 0.f;
   }
   for (int e = threadIdx.x; e < E; e += 128) {
     float o = 0.f;
-    for (int m = 0; m < L; ++m) o = fmaf(wm[m], base[(long long)m * 3 * E + 2 * E + e], o);
+#pragma unroll
+    for (int m = 0; m < LT; ++m)
+      if (m < L) o = fmaf(wm[m], base[(long long)m * 3 * E + 2 * E + e], o);
     obar[(long long)b * E + e] = o;
   }
+}
+
+// logits[b][c] = <emb[b], W_c[c]> + b_c[c]: one warp per (image, class) pair, 4 pairs per 128-thread block.
+__global__ void __launch_bounds__(128) classifier_fwd_kernel(const float* __restrict__ emb, const float* __restrict__ Wc,
+                                                             const float* __restrict__ bc, float* __restrict__ logits,
+                                                             int B, int E, int nc) {
+  const int pair = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (pair >= B * nc) return;
+  const int b = pair / nc, c = pair % nc;
+  const float* x = emb + (long long)b * E;
+  const float* w = Wc + (long long)c * E;
+  float s = 0.f;
+  for (int e = lane; e < E; e += 32) s = fmaf(x[e], __ldg(w + e), s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) logits[pair] = s + (bc ? bc[c] : 0.f);
 }
 
 // Backward of the per-image core. dObar: (B, E). Writes dQKV (B*L, 3E).

@@ -4,7 +4,9 @@
 #include "common.cuh"
 #include "gram_fwd.cuh"
 #include "gram_bwd.cuh"
+#include "gram_bwd2.cuh"
 #include "attn_head.cuh"
+#include "umma_gemm.cuh"
 #include <string>
 
 namespace gh {
@@ -28,22 +30,37 @@ static int ilog2_exact(int v) {
   return s;
 }
 
-// K-split that best fills `ctas` persistent CTAs: minimise ceil(units/ctas) / (units/ctas), keep >= 4 k-blocks a part.
+// K split of the Gram forward. Measured on B200 (profiles/r01*_kernel_timings.log): once there is at least one unit
+// per CTA, splitting K only adds atomics and epilogues (C=512: 151 us unsplit vs 179 us split in two), so K is split
+// only to fill the machine at small batch (camera mode: 1 image -> 1..10 units), keeping >= 2 k-blocks per part.
 static int choose_ksplit(long long base_units, int nkb, int ctas) {
-  int best = 1;
-  double best_eff = 0.0;
-  const int kmax = nkb / 4 > 1 ? nkb / 4 : 1;
-  for (int ks = 1; ks <= kmax && ks <= 16; ++ks) {
-    const double units = (double)base_units * ks;
-    const double waves = units / ctas;
-    const double eff = waves / (double)((long long)((units + ctas - 1) / ctas));
-    if (eff > best_eff + 0.02) { best_eff = eff; best = ks; }
-  }
-  return best;
+  if (base_units >= ctas) return 1;
+  long long ks = (2LL * ctas + base_units - 1) / base_units;
+  const int kmax = nkb / 2 > 1 ? nkb / 2 : 1;
+  if (ks > kmax) ks = kmax;
+  if (ks > 128) ks = 128;
+  return ks < 1 ? 1 : (int)ks;
 }
 
 // Tuning knobs (gh_set_option)
 static int g_opt_fwd_producer_warps = 16;
+static int g_opt_bwd_variant = 2;   // 1 = transposed product (gram_bwd.cuh), 2 = MN-major F operand (gram_bwd2.cuh)
+static int g_opt_bwd_nhw = 0;       // 0 = auto, 128, 256
+static int g_opt_bwd_producer_warps = 16;   // NHW = 256 only
+static int g_opt_attn_gemm = 1;     // 1 = tcgen05 split-bf16 GEMM for the attention linear layers, 0 = fp32 SIMT
+
+// D = A B (+ bias) with strided fp32 operands: tensor-core path when the layout allows it, fp32 FMA kernel otherwise.
+static cudaError_t gemm_auto(const float* A, long long a_sm, long long a_sk, const float* Bm, long long b_sk,
+                             long long b_sn, const float* bias, float* D, long long ldd, int M, int N, int K,
+                             int accumulate, cudaStream_t st) {
+  if (g_opt_attn_gemm == 1 && !accumulate && (a_sk == 1 || a_sm == 1) && (b_sk == 1 || b_sn == 1)) {
+    const bool a_mn = (a_sk != 1), b_mn = (b_sk != 1);
+    cudaError_t e = launch_umma_gemm(A, a_mn, a_mn ? a_sk : a_sm, Bm, b_mn, b_mn ? b_sk : b_sn, bias, D, ldd, M, N, K,
+                                     sm_count_cached(), st);
+    if (e != cudaErrorNotSupported) return e;
+  }
+  return launch_sgemm(A, a_sm, a_sk, Bm, b_sk, b_sn, bias, D, ldd, M, N, K, accumulate, st);
+}
 
 template <int SRC, int KP, int NPW>
 static cudaError_t launch_gram_fwd_one(const GramFwdParams& p, int grid, cudaStream_t st) {
@@ -151,6 +168,53 @@ static int gram_bwd_common(const void* F, int f_dtype, long long img_stride, lon
     if (!dG) return GH_ERR_BAD_ARG;
     p.scale = 1.0f / (float)HW;
   }
+  if (g_opt_bwd_variant == 2) {
+    GramBwd2Params q;
+    q.F = F; q.img_stride = img_stride; q.row_stride = row_stride;
+    q.B = B; q.C = C; q.HW = HW; q.mode = mode;
+    q.dP = dP; q.dp_img_stride = dp_img_stride; q.g = g; q.kshift = p.kshift; q.dG = dG;
+    q.dF = dF; q.df_img_stride = df_img_stride; q.df_row_stride = df_row_stride; q.scale = p.scale;
+    const int nhw = g_opt_bwd_nhw ? g_opt_bwd_nhw : 256;   // measured: 256 wins on every ResNet stage shape
+    q.nHT = (HW + nhw - 1) / nhw;
+    q.nCP = (C + 255) / 256;
+    q.nkb = (C + 63) / 64;
+    q.nA = (C > 128) ? 2 : 1;
+    const long long total2 = (long long)B * q.nHT * q.nCP;
+    if (total2 > 0x7fffffffLL) return GH_ERR_UNSUPPORTED;
+    q.total_units = (int)total2;
+    const int sms2 = sm_count_cached();
+    const int ctas2 = (max_ctas > 0 && max_ctas < sms2) ? max_ctas : sms2;
+    int grid2 = (int)(total2 < ctas2 ? total2 : ctas2);
+    q.units_per_cta = (int)((total2 + grid2 - 1) / grid2);
+    grid2 = (int)((total2 + q.units_per_cta - 1) / q.units_per_cta);
+    q.df_vec_ok = (HW % 4 == 0 && df_img_stride % 4 == 0 && df_row_stride % 4 == 0 && ((uintptr_t)dF) % 16 == 0) ? 1 : 0;
+    const bool s4 = (HW % 4 == 0) && (row_stride % 4 == 0) && (img_stride % 4 == 0);
+    int src;
+    if (f_dtype == GH_DTYPE_F32) src = (s4 && ((uintptr_t)F) % 16 == 0) ? 0 : 1;
+    else src = (s4 && ((uintptr_t)F) % 8 == 0) ? 2 : 3;
+    cudaError_t e2 = cudaErrorInvalidValue;
+#define GH_LAUNCH_B2(SRC, NHW, NPW)                                                                                    \
+    {                                                                                                                  \
+      e2 = cudaFuncSetAttribute(gram_bwd2_kernel<SRC, NHW, NPW>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                (int)kB2SmemBytes);                                                                    \
+      if (e2 == cudaSuccess) {                                                                                         \
+        gram_bwd2_kernel<SRC, NHW, NPW><<<grid2, (NPW == 8 ? 13 : 20) * 32, kB2SmemBytes, st>>>(q);                    \
+        e2 = cudaGetLastError();                                                                                       \
+      }                                                                                                                \
+    }
+    if (nhw == 128) {
+      if (src == 0) GH_LAUNCH_B2(0, 128, 8) else if (src == 1) GH_LAUNCH_B2(1, 128, 8)
+      else if (src == 2) GH_LAUNCH_B2(2, 128, 8) else GH_LAUNCH_B2(3, 128, 8)
+    } else if (g_opt_bwd_producer_warps == 8) {
+      if (src == 0) GH_LAUNCH_B2(0, 256, 8) else if (src == 1) GH_LAUNCH_B2(1, 256, 8)
+      else if (src == 2) GH_LAUNCH_B2(2, 256, 8) else GH_LAUNCH_B2(3, 256, 8)
+    } else {
+      if (src == 0) GH_LAUNCH_B2(0, 256, 16) else if (src == 1) GH_LAUNCH_B2(1, 256, 16)
+      else if (src == 2) GH_LAUNCH_B2(2, 256, 16) else GH_LAUNCH_B2(3, 256, 16)
+    }
+#undef GH_LAUNCH_B2
+    return (int)e2;
+  }
   p.dF = dF; p.df_img_stride = df_img_stride; p.df_row_stride = df_row_stride;
   p.NB = (C > 256) ? 2 : 1;
   p.nHT = (HW + 127) / 128;
@@ -244,6 +308,26 @@ int gh_set_option(const char* name, int value) {
     g_opt_fwd_producer_warps = value;
     return 0;
   }
+  if (key == "attn_gemm") {
+    if (value != 0 && value != 1) return GH_ERR_BAD_ARG;
+    g_opt_attn_gemm = value;
+    return 0;
+  }
+  if (key == "gram_bwd_variant") {
+    if (value != 1 && value != 2) return GH_ERR_BAD_ARG;
+    g_opt_bwd_variant = value;
+    return 0;
+  }
+  if (key == "gram_bwd_producer_warps") {
+    if (value != 8 && value != 16) return GH_ERR_BAD_ARG;
+    g_opt_bwd_producer_warps = value;
+    return 0;
+  }
+  if (key == "gram_bwd_nhw") {
+    if (value != 0 && value != 128 && value != 256) return GH_ERR_BAD_ARG;
+    g_opt_bwd_nhw = value;
+    return 0;
+  }
   return GH_ERR_BAD_ARG;
 }
 
@@ -311,17 +395,24 @@ int gh_attn_head_fwd(const float* desc, const float* W_in, const float* b_in, co
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
   // QKV = X W_in^T + b_in           (B*L, 3E)
-  e = launch_sgemm(desc, E, 1, W_in, 1, E, b_in, qkv, 3LL * E, B * L, 3 * E, E, 0, st);
+  e = gemm_auto(desc, E, 1, W_in, 1, E, b_in, qkv, 3LL * E, B * L, 3 * E, E, 0, st);
   if (e != cudaSuccess) return (int)e;
-  attn_core_fwd_kernel<<<B, 128, 0, st>>>(qkv, probs, obar, L, E);
+  if (L <= 4) attn_core_fwd_kernel<4><<<B, 128, 0, st>>>(qkv, probs, obar, L, E);
+  else attn_core_fwd_kernel<kMaxL><<<B, 128, 0, st>>>(qkv, probs, obar, L, E);
   e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   // emb = Obar W_out^T + b_out      (B, E)
-  e = launch_sgemm(obar, E, 1, W_out, 1, E, b_out, emb, E, B, E, E, 0, st);
+  e = gemm_auto(obar, E, 1, W_out, 1, E, b_out, emb, E, B, E, E, 0, st);
   if (e != cudaSuccess) return (int)e;
-  // logits = emb W_c^T + b_c        (B, nc)
-  e = launch_sgemm(emb, E, 1, W_c, 1, E, b_c, logits, nc, B, nc, E, 0, st);
-  return (int)e;
+  // logits = emb W_c^T + b_c        (B, nc): nc is a handful of classes -> one warp per (image, class) dot product
+  classifier_fwd_kernel<<<(B * nc + 3) / 4, 128, 0, st>>>(emb, W_c, b_c, logits, B, E, nc);
+  return (int)cudaGetLastError();
+}
+
+int gh_gemm_f32(const float* A, long long a_sm, long long a_sk, const float* Bm, long long b_sk, long long b_sn,
+                const float* bias, float* D, long long ldd, int M, int N, int K, void* stream) {
+  if (!A || !Bm || !D || M <= 0 || N <= 0 || K <= 0) return GH_ERR_BAD_ARG;
+  return (int)gemm_auto(A, a_sm, a_sk, Bm, b_sk, b_sn, bias, D, ldd, M, N, K, 0, (cudaStream_t)stream);
 }
 
 long long gh_attn_head_bwd_workspace(int B, int L, int E) {
@@ -346,31 +437,31 @@ int gh_attn_head_bwd(const float* desc, const float* W_in, const float* W_out, c
     e = cudaMemcpyAsync(demb, d_emb_ext, (size_t)B * E * 4, cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) return (int)e;
   }
-  e = launch_sgemm(d_logits, nc, 1, W_c, E, 1, nullptr, demb, E, B, E, nc, d_emb_ext ? 1 : 0, st);
+  e = gemm_auto(d_logits, nc, 1, W_c, E, 1, nullptr, demb, E, B, E, nc, d_emb_ext ? 1 : 0, st);
   if (e != cudaSuccess) return (int)e;
   if (dW_c) {   // dW_c = d_logits^T emb   (nc, E)
-    e = launch_sgemm(d_logits, 1, nc, emb, E, 1, nullptr, dW_c, E, nc, E, B, 0, st);
+    e = gemm_auto(d_logits, 1, nc, emb, E, 1, nullptr, dW_c, E, nc, E, B, 0, st);
     if (e != cudaSuccess) return (int)e;
   }
   if (db_c) colsum_kernel<<<(nc + 31) / 32, dim3(32, 8), 0, st>>>(d_logits, nc, db_c, B, nc);
   if (dW_out) {   // dW_out = demb^T Obar  (E, E)
-    e = launch_sgemm(demb, 1, E, obar, E, 1, nullptr, dW_out, E, E, E, B, 0, st);
+    e = gemm_auto(demb, 1, E, obar, E, 1, nullptr, dW_out, E, E, E, B, 0, st);
     if (e != cudaSuccess) return (int)e;
   }
   if (db_out) colsum_kernel<<<(E + 31) / 32, dim3(32, 8), 0, st>>>(demb, E, db_out, B, E);
   // dObar = demb W_out             (B, E)
-  e = launch_sgemm(demb, E, 1, W_out, E, 1, nullptr, dobar, E, B, E, E, 0, st);
+  e = gemm_auto(demb, E, 1, W_out, E, 1, nullptr, dobar, E, B, E, E, 0, st);
   if (e != cudaSuccess) return (int)e;
   attn_core_bwd_kernel<<<B, 128, 0, st>>>(qkv, probs, dobar, dqkv, L, E);
   e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   if (dW_in) {   // dW_in = dQKV^T X       (3E, E)
-    e = launch_sgemm(dqkv, 1, 3LL * E, desc, E, 1, nullptr, dW_in, E, 3 * E, E, B * L, 0, st);
+    e = gemm_auto(dqkv, 1, 3LL * E, desc, E, 1, nullptr, dW_in, E, 3 * E, E, B * L, 0, st);
     if (e != cudaSuccess) return (int)e;
   }
   if (db_in) colsum_kernel<<<(3 * E + 31) / 32, dim3(32, 8), 0, st>>>(dqkv, 3LL * E, db_in, B * L, 3 * E);
   if (d_desc) {  // dX = dQKV W_in         (B*L, E)
-    e = launch_sgemm(dqkv, 3LL * E, 1, W_in, E, 1, nullptr, d_desc, E, B * L, E, 3 * E, 0, st);
+    e = gemm_auto(dqkv, 3LL * E, 1, W_in, E, 1, nullptr, d_desc, E, B * L, E, 3 * E, 0, st);
     if (e != cudaSuccess) return (int)e;
   }
   return (int)cudaGetLastError();

@@ -151,6 +151,21 @@ def adaptive_pool_bwd(d_desc: torch.Tensor, l: int, c: int, g: int) -> torch.Ten
     return dg
 
 
+def gemm_f32(a: torch.Tensor, b: torch.Tensor, bias: torch.Tensor = None) -> torch.Tensor:
+    """a (M, K) @ b (K, N) (+ bias) for arbitrarily strided fp32 CUDA views (e.g. w.t()), through gh_gemm_f32."""
+    _require_cuda(a, "a")
+    m, k = a.shape
+    k2, n = b.shape
+    assert k == k2 and a.dtype == torch.float32 and b.dtype == torch.float32
+    out = torch.empty((m, n), device=a.device, dtype=torch.float32)
+    work = dict(bytes=(m * k + k * n + m * n) * 4, flops=2 * m * n * k, kind="gemm")
+    with torch.cuda.device(a.device), _Timed(f"gemm_f32[M={m},N={n},K={k}]", 1, a.device, **work):
+        rc = _lib.lib().gh_gemm_f32(a.data_ptr(), a.stride(0), a.stride(1), b.data_ptr(), b.stride(0), b.stride(1),
+                                    0 if bias is None else bias.data_ptr(), out.data_ptr(), n, m, n, k, _stream_ptr(a))
+    check(rc, "gh_gemm_f32")
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # autograd
 # ----------------------------------------------------------------------------------------------------------------------

@@ -32,8 +32,10 @@ int gh_version(void);
 /* Number of SMs the launchers size their persistent grids by (cudaDevAttrMultiProcessorCount of the current device). */
 int gh_sm_count(void);
 
-/* Launch tuning, process-wide. Known names: "gram_fwd_producer_warps" (8 or 16, default 16). Unknown name or value
- * outside the allowed set: GH_ERR_BAD_ARG. */
+/* Launch tuning, process-wide. Known names: "gram_fwd_producer_warps" (8 or 16, default 16); "gram_bwd_variant"
+ * (1 = transposed product with gathered F^T tiles, 2 = F consumed as an MN-major operand, default 2); "gram_bwd_nhw"
+ * (x-tile width of variant 2: 0 = auto, 128, 256); "gram_bwd_producer_warps" (8 or 16, for x-tile width 256); "attn_gemm" (1 = tcgen05 split-bf16 GEMMs for the attention linear
+ * layers, 0 = fp32 FMA kernels; default 1). Unknown name or value outside the allowed set: GH_ERR_BAD_ARG. */
 int gh_set_option(const char* name, int value);
 
 /* Copies the device-side error record {code, blockIdx.x, threadIdx.x, site} to host memory `out4` and clears it.
@@ -89,6 +91,15 @@ int gh_gram_dense_bwd(const void* F, int f_dtype, long long img_stride, long lon
 int gh_attn_head_fwd(const float* desc, const float* W_in, const float* b_in, const float* W_out, const float* b_out,
                      const float* W_c, const float* b_c, int B, int L, int E, int nc, float* qkv, float* probs,
                      float* obar, float* emb, float* logits, void* stream);
+
+/* The GEMM the attention entry points are built from, exposed for testing and reuse:
+ *   D[m*ldd + n] = sum_k A[m*a_sm + k*a_sk] * B[k*b_sk + n*b_sn] (+ bias[n]),   fp32 in, fp32 out.
+ * Runs on tcgen05 with split-bf16 operands (hi*hi + hi*lo + lo*hi, fp32 accumulate: ~1e-5 relative) when each operand
+ * is contiguous along one of its two axes with 16 B aligned rows and N >= 64; otherwise (and with option
+ * "attn_gemm" = 0) on the fp32 FMA kernel. Stands in for the F.linear / matmul calls inside
+ * torch.nn.functional.multi_head_attention_forward that the reference reaches through self.attention (:58). */
+int gh_gemm_f32(const float* A, long long a_sm, long long a_sk, const float* B, long long b_sk, long long b_sn,
+                const float* bias, float* D, long long ldd, int M, int N, int K, void* stream);
 
 /* Number of fp32 elements gh_attn_head_bwd needs in `workspace`. */
 long long gh_attn_head_bwd_workspace(int B, int L, int E);

@@ -109,4 +109,5 @@ def test_checkpoint_roundtrip_through_functions(pair, tmp_path):
     x = torch.randn(2, 3, 224, 224, device="cuda")
     with torch.no_grad():
         a, b = ours(x), other(x)
-    assert torch.equal(a[1], b[1])
+    # same weights -> same outputs up to fp32 summation order (split-K atomics, cuDNN algorithm choice)
+    assert torch.allclose(a[1], b[1], rtol=1e-3, atol=1e-4)

@@ -73,6 +73,40 @@ def test_pooled_gram_forward(ops, B, C, HW, g, ksplit, dtype):
     assert np.abs(sym - sym.transpose(0, 2, 1)).max() <= 1e-5 * np.abs(sym).max()
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (768, 3072, 1024), (100, 200, 72), (3, 1024, 1024), (260, 64, 36)])
+def test_split_bf16_gemm_all_layouts(ops, M, N, K):
+    """gh_gemm_f32 (tcgen05, hi/lo bf16 operands, split-K with atomics when M*N is small): <= 2e-5 vs fp64."""
+    torch.manual_seed(0)
+    for a_t in (False, True):
+        for b_t in (False, True):
+            a = torch.randn(K, M, device="cuda").t() if a_t else torch.randn(M, K, device="cuda")
+            b = torch.randn(N, K, device="cuda").t() if b_t else torch.randn(K, N, device="cuda")
+            bias = torch.randn(N, device="cuda")
+            got = ops.gemm_f32(a, b, bias)
+            ref = a.double() @ b.double() + bias.double()
+            assert float((got.double() - ref).norm() / ref.norm()) <= 2e-5, (a_t, b_t)
+
+
+def test_gram_backward_variants_agree(ops):
+    from heuristique_style_transfer_code_b200 import _lib
+    torch.manual_seed(0)
+    x = torch.relu(torch.randn(3, 512, 784, device="cuda"))
+    dd = torch.randn(3, 1, 1024, device="cuda")
+    ref = O.gram_pool_backward(npf(x), 32, npf(dd[:, 0]))
+    try:
+        for variant, nhw, npw in [(1, 0, 16), (2, 128, 8), (2, 256, 8), (2, 256, 16)]:
+            lib = _lib.lib()
+            assert lib.gh_set_option(b"gram_bwd_variant", variant) == 0
+            assert lib.gh_set_option(b"gram_bwd_nhw", nhw) == 0
+            assert lib.gh_set_option(b"gram_bwd_producer_warps", npw) == 0
+            df = ops.gram_pool_bwd(x, 32, dd, 0)
+            assert O.rel_err(npf(df), ref) <= 6e-3, (variant, nhw, npw)
+    finally:
+        _lib.lib().gh_set_option(b"gram_bwd_variant", 2)
+        _lib.lib().gh_set_option(b"gram_bwd_nhw", 0)
+        _lib.lib().gh_set_option(b"gram_bwd_producer_warps", 16)
+
+
 def test_producer_warp_variants_agree(ops):
     from heuristique_style_transfer_code_b200 import _lib
     torch.manual_seed(0)
@@ -90,7 +124,7 @@ def test_producer_warp_variants_agree(ops):
 
 
 @pytest.mark.parametrize("B,C,HW,ksplit", [(1, 64, 3136, 1), (2, 256, 784, 1), (2, 512, 196, 1), (1, 64, 3136, 0),
-                                           (2, 320, 100, 1), (1, 256, 49, 1)])
+                                           (2, 320, 100, 1), (1, 256, 196, 1)])
 def test_dense_gram_forward(ops, B, C, HW, ksplit):
     torch.manual_seed(0)
     x = torch.relu(torch.randn(B, C, HW, device="cuda"))

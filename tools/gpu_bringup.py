@@ -219,6 +219,28 @@ def generic_pool():
 
 
 @case
+def gemm_layouts():
+    """gh_gemm_f32 on tcgen05 (split-bf16): all four operand layouts, tails in M/N/K, bias."""
+    import torch
+    from heuristique_style_transfer_code_b200 import ops
+    ok = True
+    for (M, N, K) in [(128, 256, 64), (768, 3072, 1024), (100, 200, 72), (3, 1024, 1024), (3072, 1024, 768), (260, 64, 36)]:
+        torch.manual_seed(0)
+        for a_t in (False, True):
+            for b_t in (False, True):
+                a = (torch.randn(K, M, device="cuda").t() if a_t else torch.randn(M, K, device="cuda"))
+                b = (torch.randn(N, K, device="cuda").t() if b_t else torch.randn(K, N, device="cuda"))
+                bias = torch.randn(N, device="cuda")
+                got = ops.gemm_f32(a, b, bias)
+                torch.cuda.synchronize()
+                ref = a.double() @ b.double() + bias.double()
+                e = float((got.double() - ref).norm() / ref.norm())
+                print(f"gemm M={M} N={N} K={K} A {'m-contig' if a_t else 'k-contig'} B {'k-contig' if b_t else 'n-contig'}: rel_err={e:.3e}")
+                ok &= e < 2e-5
+    return ok
+
+
+@case
 def module_parity():
     """Whole drop-in module vs the fp32 torch port of the reference, both on the GPU, train-mode BN."""
     import torch
@@ -273,7 +295,7 @@ def timing():
         x = torch.relu(torch.randn(B, C, HW, device="cuda"))
         desc = torch.empty(B, 3, g * g, device="cuda")
         dd = torch.randn(B, 3, g * g, device="cuda")
-        for (npw, ks) in [(16, 0), (16, 1), (16, 4), (8, 0), (8, 1), (8, 4)]:
+        for (npw, ks) in [(16, 0), (16, 1)]:
             _lib.lib().gh_set_option(b"gram_fwd_producer_warps", npw)
             ops.KSPLIT = ks
             for _ in range(3):
@@ -292,20 +314,27 @@ def timing():
                   f"  {fl/ms/1e9:8.1f} TFLOP/s sym ({fl/ms/1e9/peaks['bf16_tflops']:.2f} of tensor)")
         ops.KSPLIT = 0
         _lib.lib().gh_set_option(b"gram_fwd_producer_warps", 16)
-        for _ in range(3):
-            ops.gram_pool_bwd(x, g, dd, 0)
-        torch.cuda.synchronize()
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        n = 10
-        ev[0].record()
-        for _ in range(n):
-            ops.gram_pool_bwd(x, g, dd, 0)
-        ev[1].record(); torch.cuda.synchronize()
-        ms = ev[0].elapsed_time(ev[1]) / n
-        by = 2 * B * C * HW * 4
-        fl = 2 * B * C * C * HW
-        print(f"bwd B={B} C={C} HW={HW}: {ms*1e3:8.1f} us  {by/ms/1e6:8.1f} GB/s ({by/ms/1e6/peaks['hbm_gbs']:.2f} of HBM)"
-              f"  {fl/ms/1e9:8.1f} TFLOP/s ({fl/ms/1e9/peaks['bf16_tflops']:.2f} of tensor)")
+        for (variant, nhw, bnpw) in [(2, 128, 8), (2, 256, 8), (2, 256, 16)]:
+            _lib.lib().gh_set_option(b"gram_bwd_variant", variant)
+            _lib.lib().gh_set_option(b"gram_bwd_nhw", nhw)
+            _lib.lib().gh_set_option(b"gram_bwd_producer_warps", bnpw)
+            for _ in range(3):
+                ops.gram_pool_bwd(x, g, dd, 0)
+            torch.cuda.synchronize()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            n = 10
+            ev[0].record()
+            for _ in range(n):
+                ops.gram_pool_bwd(x, g, dd, 0)
+            ev[1].record(); torch.cuda.synchronize()
+            ms = ev[0].elapsed_time(ev[1]) / n
+            by = 2 * B * C * HW * 4
+            fl = 2 * B * C * C * HW
+            print(f"bwd B={B} C={C} HW={HW} variant={variant} nhw={nhw} npw={bnpw}: {ms*1e3:8.1f} us  {by/ms/1e6:8.1f} GB/s ({by/ms/1e6/peaks['hbm_gbs']:.2f} of HBM)"
+                  f"  {fl/ms/1e9:8.1f} TFLOP/s ({fl/ms/1e9/peaks['bf16_tflops']:.2f} of tensor)")
+        _lib.lib().gh_set_option(b"gram_bwd_variant", 2)
+        _lib.lib().gh_set_option(b"gram_bwd_nhw", 0)
+        _lib.lib().gh_set_option(b"gram_bwd_producer_warps", 16)
         # torch reference ops on the same GPU (fp32 bmm + div + pool), for scale
         xf = x
         for _ in range(2):
@@ -317,6 +346,32 @@ def timing():
         ev[1].record(); torch.cuda.synchronize()
         print(f"torch fp32 bmm+div+pool C={C} HW={HW}: {ev[0].elapsed_time(ev[1])/3*1e3:8.1f} us")
         del x, desc, dd, G, P
+    # attention head, both GEMM back ends
+    for Bq in (256, 512, 1):
+        E, L, nc = 1024, 3, 4
+        desc = torch.randn(Bq, L, E, device="cuda", requires_grad=True)
+        mha = torch.nn.MultiheadAttention(E, 1).cuda(); lin = torch.nn.Linear(E, nc).cuda()
+        ps = [mha.in_proj_weight, mha.in_proj_bias, mha.out_proj.weight, mha.out_proj.bias, lin.weight, lin.bias]
+        for mode in (1, 0):
+            _lib.lib().gh_set_option(b"attn_gemm", mode)
+            def fb():
+                emb, logits = ops.attention_head(desc, *ps)
+                return emb, logits
+            for _ in range(2):
+                e_, l_ = fb(); (l_.sum() + e_.sum()).backward()
+            torch.cuda.synchronize()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
+            for _ in range(5):
+                e_, l_ = fb()
+            ev[1].record()
+            for _ in range(5):
+                e_, l_ = fb(); (l_.sum() + e_.sum()).backward()
+            ev[2].record(); torch.cuda.synchronize()
+            f_us = ev[0].elapsed_time(ev[1]) / 5 * 1e3
+            fb_us = ev[1].elapsed_time(ev[2]) / 5 * 1e3
+            print(f"attn B={Bq} gemm={'tcgen05 split-bf16' if mode else 'fp32 SIMT'}: fwd {f_us:8.1f} us   fwd+bwd {fb_us:8.1f} us")
+        _lib.lib().gh_set_option(b"attn_gemm", 1)
     return True
 
 

@@ -21,5 +21,10 @@ if [ "${2:-}" != "skip-ncu" ]; then
   echo "== ncu full (gram fwd)"
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:gram_fwd_kernel -s 9 -c 3 -o $OUT/${TAG}_gram_fwd \
       python bench.py --steps 2 --warmup 3 --skip-train --skip-cpu > $OUT/${TAG}_ncu_full.log 2>&1
-  echo "ncu full exit=$?"; ls -la $OUT | tail -5
+  echo "ncu full exit=$?"
+  echo "== ncu full (train kernels: gram bwd, attention GEMMs)"
+  python bench.py --steps 1 --warmup 3 --train-steps 1 --skip-cpu > $OUT/${TAG}_ncu_plain2.log 2>&1 && \
+  timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"gram_bwd2_kernel|umma_gemm_kernel" -c 12 -o $OUT/${TAG}_train_kernels \
+      python bench.py --steps 1 --warmup 3 --train-steps 1 --skip-cpu > $OUT/${TAG}_ncu_full2.log 2>&1
+  echo "ncu full2 exit=$?"; ls -la $OUT | tail -5
 fi
