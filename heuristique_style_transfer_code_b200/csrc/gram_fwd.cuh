@@ -234,6 +234,96 @@ __device__ __forceinline__ void gram_epi_pool_chunk(const float (&v)[32], int c_
   }
 }
 
+// Sum of CW consecutive registers starting at v[o], as a balanced tree (short dependency chain).
+template <int CW>
+__device__ __forceinline__ float tree_sum(const uint32_t (&v)[32], int o) {
+  if constexpr (CW == 1) {
+    return __uint_as_float(v[o]);
+  } else {
+    return tree_sum<CW / 2>(v, o) + tree_sum<CW / 2>(v, o + CW / 2);
+  }
+}
+
+// Pooled epilogue for a group of 128 accumulator columns (4 tcgen05.ld of 32 columns, two in flight at a time), KP >= 8.
+// Thread = Gram row c_row. Column pooling is in-thread; row pooling over LK = min(KP, 32) lanes is a halving butterfly:
+// at each step a lane hands half of its partial sums to its partner and keeps the other half, so NV values cost
+// NV - 1 + (log2 LK - log2 NV) shuffles instead of NV * log2 LK, and every lane ends up owning distinct outputs.
+template <int KP>
+__device__ __forceinline__ void gram_epi_pool_group128(uint32_t taddr, int c_row, int c_col0, int C, int g, float scale,
+                                                       float* __restrict__ outp, bool mirror, bool atomics, int lane) {
+  constexpr int CW = KP < 32 ? KP : 32;         // columns summed in-thread per tcgen05.ld chunk value
+  constexpr int NCc = 32 / CW;                  // values per 32-column chunk
+  constexpr int CPV = KP > 32 ? KP / 32 : 1;    // chunks that fold into one value (KP = 64: 2, 128: 4)
+  constexpr int NV = 4 * NCc / CPV;             // values per thread for the 128-column group
+  constexpr int LK = KP < 32 ? KP : 32;
+  float s[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) s[j] = 0.f;
+#pragma unroll
+  for (int pair = 0; pair < 2; ++pair) {
+    uint32_t v0[32], v1[32];
+    tmem_ld32_nowait(taddr + (uint32_t)(pair * 64), v0);
+    tmem_ld32_nowait(taddr + (uint32_t)(pair * 64 + 32), v1);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < NCc; ++j) {
+      s[((2 * pair) * NCc + j) / CPV] += tree_sum<CW>(v0, j * CW);
+      s[((2 * pair + 1) * NCc + j) / CPV] += tree_sum<CW>(v1, j * CW);
+    }
+  }
+  int nv = NV, base = 0;
+#pragma unroll
+  for (int off = LK / 2; off >= 1; off >>= 1) {
+    if (nv > 1) {
+      const int half = nv >> 1;
+      const bool upper = (lane & off) != 0;
+#pragma unroll
+      for (int j = 0; j < NV / 2; ++j) {
+        if (j < half) {
+          const float send = upper ? s[j] : s[j + half];
+          const float keep = upper ? s[j + half] : s[j];
+          s[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      if (upper) base += half;
+      nv = half;
+    } else {
+      s[0] += __shfl_xor_sync(0xffffffffu, s[0], off);
+    }
+  }
+  // lanes that went through plain (non-halving) steps hold copies: the one with those low lane bits clear writes
+  constexpr int kHalvings = (NV >= LK) ? /*all steps halve*/ 31 : 0;
+  (void)kHalvings;
+  int plain_mask = 0;
+  {
+    int n2 = NV;
+#pragma unroll
+    for (int off = LK / 2; off >= 1; off >>= 1) {
+      if (n2 > 1) n2 >>= 1;
+      else plain_mask |= off;
+    }
+  }
+  if ((lane & plain_mask) != 0 || c_row >= C) return;
+  const int pi = c_row / KP;
+#pragma unroll
+  for (int t = 0; t < NV; ++t) {
+    if (t < nv) {
+      const int jv = base + t;
+      if (c_col0 + jv * KP < C) {
+        const int pj = c_col0 / KP + jv;
+        const float val = s[t] * scale;
+        if (atomics) {
+          red_add_f32(outp + pi * g + pj, val);
+          if (mirror) red_add_f32(outp + pj * g + pi, val);
+        } else {
+          outp[pi * g + pj] = val;
+          if (mirror) outp[pj * g + pi] = val;
+        }
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ void gram_epi_dense_chunk(const float (&v)[32], int c_row, int c_col0, int C, float scale,
                                                      float* __restrict__ G, bool mirror, bool atomics) {
   if (c_row >= C) return;
@@ -263,14 +353,16 @@ __device__ __forceinline__ void gram_epi_dense_chunk(const float (&v)[32], int c
 }
 
 // SRC: see gf_load.  KP = pool factor (POOL) or 0 (DENSE).  NPW = producer warps (8 or 16).
-// Warp roles: [0, NPW) producers, [NPW, NPW+4) epilogue (NPW % 4 == 0 so warp % 4 is the TMEM lane quarter). The first
+// NEW = epilogue warps (4 or 8).
+// Warp roles: [0, NPW) producers, [NPW, NPW+NEW) epilogue (NPW % 4 == 0 so warp % 4 is the TMEM lane quarter). The first
 // epilogue warp also owns TMEM and issues the MMAs of a unit before joining its epilogue: with one accumulator set in
 // TMEM (384-512 of the 512 columns) the two phases of a unit cannot overlap anyway, and NPW + 4 warps (a multiple of
 // the 4 SM sub-partitions) leaves every thread 96 (NPW = 16) / 168 (NPW = 8) registers for the double-buffered loads.
-template <int SRC, int KP, int NPW>
-__global__ void __launch_bounds__((NPW + 4) * 32, 1) gram_fwd_kernel(const GramFwdParams p) {
+template <int SRC, int KP, int NPW, int NEW>
+__global__ void __launch_bounds__((NPW + NEW) * 32, 1) gram_fwd_kernel(const GramFwdParams p) {
   constexpr int NT = NPW * 32;
   constexpr int kEpiWarp0 = NPW, kMmaWarp = NPW;
+  static_assert(NEW == 4 || NEW == 8, "4 or 8 epilogue warps");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = smem_base + kGfStages * kGfStageBytes;
@@ -289,7 +381,7 @@ __global__ void __launch_bounds__((NPW + 4) * 32, 1) gram_fwd_kernel(const GramF
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_tfull, 1);
-    mbar_init(bar_tempty, 4);
+    mbar_init(bar_tempty, NEW);
     mbar_fence_init();
   }
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, kGfTmemCols);
@@ -319,7 +411,9 @@ __global__ void __launch_bounds__((NPW + 4) * 32, 1) gram_fwd_kernel(const GramF
     }
   } else {
     // =========================== MMA issue (first warp) + epilogue (all four) ===========================
-    const int q = warp - kEpiWarp0;   // TMEM lane quarter this warp may read (= warp % 4)
+    const int ew = warp - kEpiWarp0;
+    const int q = ew & 3;             // TMEM lane quarter this warp may read (= warp % 4)
+    const int hc = ew >> 2;           // with 8 epilogue warps, the two warps of a quarter alternate 128-column groups
     uint32_t acc_phase = 0;
     uint32_t stage = 0, phase = 0;
     const uint32_t idesc256 = make_idesc_bf16(128, 256), idesc128 = make_idesc_bf16(128, 128);
@@ -327,7 +421,7 @@ __global__ void __launch_bounds__((NPW + 4) * 32, 1) gram_fwd_kernel(const GramF
     for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
       const GramUnit w = gram_decode_unit(p, u);
       const bool diag = (w.I == w.J);
-      if (q == 0) {
+      if (ew == 0) {
         mbar_wait(bar_tempty, acc_phase ^ 1u, 200u);   // all four warps have drained the previous unit's accumulators
         tc_fence_after_sync();
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
@@ -381,16 +475,26 @@ __global__ void __launch_bounds__((NPW + 4) * 32, 1) gram_fwd_kernel(const GramF
         const int colbase = w.J * 256 + ((a == 1 && diag) ? 128 : 0);
         if (w.I * 256 + a * 128 >= p.C) break;   // whole accumulator is padding (C <= 128)
 #pragma unroll 1
-        for (int n0 = 0; n0 < ncols; n0 += 32) {
-          const int c_col0 = colbase + n0;
-          if (c_col0 >= p.C) break;              // padding columns
-          float v[32];
-          tmem_ld32(lane_addr + (uint32_t)(a * 256 + n0), v);
+        for (int g0 = hc * 128; g0 < ncols; g0 += 128 * (NEW / 4)) {
+          const int c_grp = colbase + g0;
+          if (c_grp >= p.C) break;              // padding columns
           // a 128x128 block strictly above the diagonal is mirrored; diagonal blocks are complete on their own
-          const bool mirror = (c_col0 >> 7) > (c_row >> 7);
-          if (KP > 0)
-            gram_epi_pool_chunk<(KP > 0 ? KP : 1)>(v, c_row, c_col0, p.C, p.g, p.scale, outp, mirror, atomics, lane);
-          else gram_epi_dense_chunk(v, c_row, c_col0, p.C, p.scale, outp, mirror, atomics);
+          const bool mirror = (c_grp >> 7) > (c_row >> 7);
+          if constexpr (KP >= 8) {
+            gram_epi_pool_group128<KP>(lane_addr + (uint32_t)(a * 256 + g0), c_row, c_grp, p.C, p.g, p.scale, outp, mirror,
+                                       atomics, lane);
+          } else {
+#pragma unroll 1
+            for (int n0 = 0; n0 < 128; n0 += 32) {
+              const int c_col0 = c_grp + n0;
+              if (c_col0 >= p.C) break;
+              float v[32];
+              tmem_ld32(lane_addr + (uint32_t)(a * 256 + g0 + n0), v);
+              if (KP > 0)
+                gram_epi_pool_chunk<(KP > 0 ? KP : 1)>(v, c_row, c_col0, p.C, p.g, p.scale, outp, mirror, atomics, lane);
+              else gram_epi_dense_chunk(v, c_row, c_col0, p.C, p.scale, outp, mirror, atomics);
+            }
+          }
         }
       }
       tc_fence_before_sync();

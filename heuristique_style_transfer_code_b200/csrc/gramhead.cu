@@ -43,7 +43,8 @@ static int choose_ksplit(long long base_units, int nkb, int ctas) {
 }
 
 // Tuning knobs (gh_set_option)
-static int g_opt_fwd_producer_warps = 16;
+static int g_opt_fwd_producer_warps = 0;    // 0 = auto
+static int g_opt_fwd_epilogue_warps = 0;    // 0 = auto
 static int g_opt_bwd_variant = 2;   // 1 = transposed product (gram_bwd.cuh), 2 = MN-major F operand (gram_bwd2.cuh)
 static int g_opt_bwd_nhw = 0;       // 0 = auto, 128, 256
 static int g_opt_bwd_producer_warps = 16;   // NHW = 256 only
@@ -62,27 +63,29 @@ static cudaError_t gemm_auto(const float* A, long long a_sm, long long a_sk, con
   return launch_sgemm(A, a_sm, a_sk, Bm, b_sk, b_sn, bias, D, ldd, M, N, K, accumulate, st);
 }
 
-template <int SRC, int KP, int NPW>
+template <int SRC, int KP, int NPW, int NEW>
 static cudaError_t launch_gram_fwd_one(const GramFwdParams& p, int grid, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(gram_fwd_kernel<SRC, KP, NPW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(gram_fwd_kernel<SRC, KP, NPW, NEW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kGfSmemBytes);
   if (e != cudaSuccess) return e;
-  gram_fwd_kernel<SRC, KP, NPW><<<grid, (NPW + 4) * 32, kGfSmemBytes, st>>>(p);
+  gram_fwd_kernel<SRC, KP, NPW, NEW><<<grid, (NPW + NEW) * 32, kGfSmemBytes, st>>>(p);
   return cudaGetLastError();
 }
 
 template <int SRC>
 static cudaError_t launch_gram_fwd_kp(const GramFwdParams& p, int kp, int grid, cudaStream_t st) {
+  // Warp mix (profiles/r01d: the C = 256 stage waits on HBM loads -> 16 producer warps; from C = 512 on the K loop is
+  // short and the TMEM drain + pooling bounds the unit time -> 8 epilogue warps). gh_set_option overrides.
+  const int npw = g_opt_fwd_producer_warps ? g_opt_fwd_producer_warps : 16;
+  const int nepi = g_opt_fwd_epilogue_warps ? g_opt_fwd_epilogue_warps : (p.C >= 512 ? 8 : 4);
 #define GH_LAUNCH_GF(KP)                                                                  \
   {                                                                                       \
-    if (g_opt_fwd_producer_warps == 8) return launch_gram_fwd_one<SRC, KP, 8>(p, grid, st); \
-    return launch_gram_fwd_one<SRC, KP, 16>(p, grid, st);                                 \
+    if (npw == 8) return launch_gram_fwd_one<SRC, KP, 8, 4>(p, grid, st);                 \
+    if (nepi == 4) return launch_gram_fwd_one<SRC, KP, 16, 4>(p, grid, st);               \
+    return launch_gram_fwd_one<SRC, KP, 16, 8>(p, grid, st);                              \
   }
   switch (kp) {
     case 0: GH_LAUNCH_GF(0)
-    case 1: GH_LAUNCH_GF(1)
-    case 2: GH_LAUNCH_GF(2)
-    case 4: GH_LAUNCH_GF(4)
     case 8: GH_LAUNCH_GF(8)
     case 16: GH_LAUNCH_GF(16)
     case 32: GH_LAUNCH_GF(32)
@@ -102,7 +105,7 @@ static int gram_fwd_common(const void* F, int f_dtype, long long img_stride, lon
   if (mode == GRAM_POOL) {
     if (g <= 0 || C % g != 0) return GH_ERR_UNSUPPORTED;
     kp = C / g;
-    if (ilog2_exact(kp) < 0 || kp > 128) return GH_ERR_UNSUPPORTED;
+    if (ilog2_exact(kp) < 0 || kp > 128 || kp < 8) return GH_ERR_UNSUPPORTED;
   }
   GramFwdParams p;
   p.F = F; p.img_stride = img_stride; p.row_stride = row_stride;
@@ -304,8 +307,13 @@ int gh_set_option(const char* name, int value) {
   if (!name) return GH_ERR_BAD_ARG;
   const std::string key(name);
   if (key == "gram_fwd_producer_warps") {
-    if (value != 8 && value != 16) return GH_ERR_BAD_ARG;
+    if (value != 0 && value != 8 && value != 16) return GH_ERR_BAD_ARG;
     g_opt_fwd_producer_warps = value;
+    return 0;
+  }
+  if (key == "gram_fwd_epilogue_warps") {
+    if (value != 0 && value != 4 && value != 8) return GH_ERR_BAD_ARG;
+    g_opt_fwd_epilogue_warps = value;
     return 0;
   }
   if (key == "attn_gemm") {

@@ -76,11 +76,11 @@ def _feature_view(x: torch.Tensor) -> Tuple[torch.Tensor, int, int, int, int, in
 
 
 def pooled_supported(c: int, g: int) -> bool:
-    """True when the fused Gram+pool kernels apply (bins are disjoint k x k blocks with k a power of two <= 128)."""
+    """True when the fused Gram+pool kernels apply (bins are disjoint k x k blocks, k a power of two in [8, 128])."""
     if g <= 0 or c % g:
         return False
     k = c // g
-    return k <= 128 and (k & (k - 1)) == 0
+    return 8 <= k <= 128 and (k & (k - 1)) == 0
 
 
 # ----------------------------------------------------------------------------------------------------------------------

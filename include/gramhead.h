@@ -32,7 +32,8 @@ int gh_version(void);
 /* Number of SMs the launchers size their persistent grids by (cudaDevAttrMultiProcessorCount of the current device). */
 int gh_sm_count(void);
 
-/* Launch tuning, process-wide. Known names: "gram_fwd_producer_warps" (8 or 16, default 16); "gram_bwd_variant"
+/* Launch tuning, process-wide. Known names: "gram_fwd_producer_warps" (0 = auto, 8, 16) and
+ * "gram_fwd_epilogue_warps" (0 = auto, 4, 8); "gram_bwd_variant"
  * (1 = transposed product with gathered F^T tiles, 2 = F consumed as an MN-major operand, default 2); "gram_bwd_nhw"
  * (x-tile width of variant 2: 0 = auto, 128, 256); "gram_bwd_producer_warps" (8 or 16, for x-tile width 256); "attn_gemm" (1 = tcgen05 split-bf16 GEMMs for the attention linear
  * layers, 0 = fp32 FMA kernels; default 1). Unknown name or value outside the allowed set: GH_ERR_BAD_ARG. */
@@ -48,7 +49,7 @@ int gh_last_device_error(unsigned int* out4);
  *   stack/flatten (layout):   :54-55
  * F: (B, C, HW) features, element (b,c,x) at F[b*img_stride + c*row_stride + x], dtype f_dtype.
  * desc: (B, L, g*g) fp32; this call overwrites desc[:, l, :] with vec_rowmajor(pool_g(F F^T / HW)).
- * Requires C % g == 0 and k = C/g a power of two <= 128 (returns GH_ERR_UNSUPPORTED otherwise: use
+ * Requires C % g == 0 and k = C/g a power of two in [8, 128] (returns GH_ERR_UNSUPPORTED otherwise: use
  * gh_gram_dense_fwd + gh_adaptive_pool_fwd, which implement torch's general bin rule).
  * ksplit: number of K (=HW) partitions per tile whose partial sums meet in fp32 atomics; 0 = choose for load balance,
  * 1 = deterministic summation order. max_ctas: 0 = one persistent CTA per SM. */

@@ -46,6 +46,9 @@ def test_argument_validation_without_gpu(library):
     assert library.gh_gram_pool_fwd(dummy, 0, 0, 0, 1, 96, 64, 32, dummy, 0, 1, 0, 0, None) == _lib.GH_ERR_UNSUPPORTED
     assert library.gh_gram_pool_fwd(dummy, 0, 0, 0, 1, 100, 64, 32, dummy, 0, 1, 0, 0, None) == _lib.GH_ERR_UNSUPPORTED
     assert library.gh_gram_pool_fwd(dummy, 7, 0, 0, 1, 256, 64, 32, dummy, 0, 1, 0, 0, None) == _lib.GH_ERR_BAD_ARG
+    assert library.gh_gram_pool_fwd(dummy, 0, 0, 0, 1, 128, 64, 32, dummy, 0, 1, 0, 0, None) == _lib.GH_ERR_UNSUPPORTED   # k = 4
+    assert library.gh_set_option(b"no_such_option", 1) == _lib.GH_ERR_BAD_ARG
+    assert library.gh_set_option(b"gram_fwd_producer_warps", 12) == _lib.GH_ERR_BAD_ARG
     assert library.gh_attn_head_bwd_workspace(4, 3, 64) == 2 * 4 * 64 + 3 * 4 * 3 * 64
 
 
