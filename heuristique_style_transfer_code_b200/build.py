@@ -7,7 +7,8 @@ import subprocess
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB_PATH = os.path.join(CSRC, "libgramhead.so")
-SOURCES = ["gramhead.cu", "common.cuh", "gram_fwd.cuh", "gram_bwd.cuh", "attn_head.cuh"]
+SOURCES = ["gramhead.cu", "common.cuh", "gram_fwd.cuh", "gram_fwd_tma.cuh", "gram_bwd.cuh", "gram_bwd2.cuh",
+           "umma_gemm.cuh", "attn_head.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -259,16 +259,29 @@ __device__ __forceinline__ void gram_epi_pool_group128(uint32_t taddr, int c_row
   float s[NV];
 #pragma unroll
   for (int j = 0; j < NV; ++j) s[j] = 0.f;
+  if constexpr (NV <= 8) {
+    // two TMEM loads in flight (64 registers): the short-K shapes (C >= 512) are bounded by this drain
 #pragma unroll
-  for (int pair = 0; pair < 2; ++pair) {
-    uint32_t v0[32], v1[32];
-    tmem_ld32_nowait(taddr + (uint32_t)(pair * 64), v0);
-    tmem_ld32_nowait(taddr + (uint32_t)(pair * 64 + 32), v1);
-    tmem_ld_wait();
+    for (int pair = 0; pair < 2; ++pair) {
+      uint32_t v0[32], v1[32];
+      tmem_ld32_nowait(taddr + (uint32_t)(pair * 64), v0);
+      tmem_ld32_nowait(taddr + (uint32_t)(pair * 64 + 32), v1);
+      tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < NCc; ++j) {
-      s[((2 * pair) * NCc + j) / CPV] += tree_sum<CW>(v0, j * CW);
-      s[((2 * pair + 1) * NCc + j) / CPV] += tree_sum<CW>(v1, j * CW);
+      for (int j = 0; j < NCc; ++j) {
+        s[((2 * pair) * NCc + j) / CPV] += tree_sum<CW>(v0, j * CW);
+        s[((2 * pair + 1) * NCc + j) / CPV] += tree_sum<CW>(v1, j * CW);
+      }
+    }
+  } else {
+    // KP = 8 (C = 256, long K loop, epilogue off the critical path): one load at a time keeps the kernel spill-free
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      uint32_t v0[32];
+      tmem_ld32_nowait(taddr + (uint32_t)(ch * 32), v0);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < NCc; ++j) s[(ch * NCc + j) / CPV] += tree_sum<CW>(v0, j * CW);
     }
   }
   int nv = NV, base = 0;
@@ -352,6 +365,94 @@ __device__ __forceinline__ void gram_epi_dense_chunk(const float (&v)[32], int c
   }
 }
 
+// MMAs of one unit, issued by lane 0 of the calling warp (all lanes wait on the barriers).
+__device__ __forceinline__ void gf_issue_unit(const GramFwdParams& p, const GramUnit& w, uint32_t smem_base,
+                                              uint32_t bar_full, uint32_t bar_empty, uint32_t bar_tfull,
+                                              uint32_t bar_tempty, uint32_t tmem_base, uint32_t& stage, uint32_t& phase,
+                                              uint32_t acc_phase, int lane) {
+  const uint32_t idesc256 = make_idesc_bf16(128, 256), idesc128 = make_idesc_bf16(128, 128);
+  const bool diag = (w.I == w.J);
+  mbar_wait(bar_tempty, acc_phase ^ 1u, 200u);   // every epilogue warp has drained the previous unit's accumulators
+  tc_fence_after_sync();
+  for (int kb = w.kb0; kb < w.kb1; ++kb) {
+    const uint32_t sA = stage;
+    mbar_wait(bar_full + 8 * sA, phase, 300u + sA);
+    uint32_t sB = sA, phaseB = phase;
+    if (!diag) {
+      sB = sA + 1;
+      if (sB == kGfStages) { sB = 0; phaseB ^= 1u; }
+      mbar_wait(bar_full + 8 * sB, phaseB, 310u + sB);
+    }
+    tc_fence_after_sync();
+    if (lane == 0) {
+      const uint32_t aI = smem_base + sA * kGfStageBytes;   // rows of block I
+      const uint32_t aJ = smem_base + sB * kGfStageBytes;   // rows of block J (== I on the diagonal)
+      const uint32_t acc = (kb > w.kb0) ? 1u : 0u;
+#pragma unroll
+      for (uint32_t ks = 0; ks < kTileK / kUmmaK; ++ks) {
+        if ((int)(kb * 64 + ks * 16) >= p.HW) break;        // K tail: whole k-steps past HW are skipped
+        const uint32_t koff = ks * 32u;
+        // acc0: I rows 0-127 x J rows 0-255
+        umma_bf16(tmem_base + 0u, make_smem_desc_sw128(aI + koff), make_smem_desc_sw128(aJ + koff), idesc256, acc | ks);
+        if (diag) {
+          // acc1: I rows 128-255 x I rows 128-255 (the lower-left 128x128 block is never computed)
+          umma_bf16(tmem_base + 256u, make_smem_desc_sw128(aI + 128u * kRowBytes + koff),
+                    make_smem_desc_sw128(aI + 128u * kRowBytes + koff), idesc128, acc | ks);
+        } else {
+          // acc1: I rows 128-255 x J rows 0-255
+          umma_bf16(tmem_base + 256u, make_smem_desc_sw128(aI + 128u * kRowBytes + koff),
+                    make_smem_desc_sw128(aJ + koff), idesc256, acc | ks);
+        }
+      }
+      umma_commit(bar_empty + 8 * sA);
+      if (!diag) umma_commit(bar_empty + 8 * sB);
+      if (kb + 1 == w.kb1) umma_commit(bar_tfull);
+    }
+    __syncwarp();
+    stage = sB + 1; phase = phaseB;
+    if (stage == kGfStages) { stage = 0; phase ^= 1u; }
+  }
+}
+
+// Drains the accumulators of one unit. q = TMEM lane quarter of this warp, hc / nhc = which of the nhc warps sharing a
+// quarter this is (they alternate 128-column groups).
+template <int KP>
+__device__ __forceinline__ void gf_epilogue_unit(const GramFwdParams& p, const GramUnit& w, uint32_t tmem_base, int q,
+                                                 int hc, int nhc, bool atomics, int lane) {
+  const bool diag = (w.I == w.J);
+  float* outp = p.out + (long long)w.b * p.out_img_stride;
+  const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+  for (int a = 0; a < 2; ++a) {
+    const int c_row = w.I * 256 + a * 128 + q * 32 + lane;
+    const int ncols = (a == 1 && diag) ? 128 : 256;
+    const int colbase = w.J * 256 + ((a == 1 && diag) ? 128 : 0);
+    if (w.I * 256 + a * 128 >= p.C) break;   // whole accumulator is padding (C <= 128)
+#pragma unroll 1
+    for (int g0 = hc * 128; g0 < ncols; g0 += 128 * nhc) {
+      const int c_grp = colbase + g0;
+      if (c_grp >= p.C) break;              // padding columns
+      // a 128x128 block strictly above the diagonal is mirrored; diagonal blocks are complete on their own
+      const bool mirror = (c_grp >> 7) > (c_row >> 7);
+      if constexpr (KP >= 8) {
+        gram_epi_pool_group128<KP>(lane_addr + (uint32_t)(a * 256 + g0), c_row, c_grp, p.C, p.g, p.scale, outp, mirror,
+                                   atomics, lane);
+      } else {
+#pragma unroll 1
+        for (int n0 = 0; n0 < 128; n0 += 32) {
+          const int c_col0 = c_grp + n0;
+          if (c_col0 >= p.C) break;
+          float v[32];
+          tmem_ld32(lane_addr + (uint32_t)(a * 256 + g0 + n0), v);
+          if (KP > 0)
+            gram_epi_pool_chunk<(KP > 0 ? KP : 1)>(v, c_row, c_col0, p.C, p.g, p.scale, outp, mirror, atomics, lane);
+          else gram_epi_dense_chunk(v, c_row, c_col0, p.C, p.scale, outp, mirror, atomics);
+        }
+      }
+    }
+  }
+}
+
 // SRC: see gf_load.  KP = pool factor (POOL) or 0 (DENSE).  NPW = producer warps (8 or 16).
 // NEW = epilogue warps (4 or 8).
 // Warp roles: [0, NPW) producers, [NPW, NPW+NEW) epilogue (NPW % 4 == 0 so warp % 4 is the TMEM lane quarter). The first
@@ -410,93 +511,19 @@ __global__ void __launch_bounds__((NPW + NEW) * 32, 1) gram_fwd_kernel(const Gra
       gf_publish<SRC, NT>(p, n1, rb, smem_base, bar_full, bar_empty, stage, phase, tid, lane);
     }
   } else {
-    // =========================== MMA issue (first warp) + epilogue (all four) ===========================
+    // =========================== MMA issue (first epilogue warp) + epilogue (all of them) ===========================
     const int ew = warp - kEpiWarp0;
     const int q = ew & 3;             // TMEM lane quarter this warp may read (= warp % 4)
     const int hc = ew >> 2;           // with 8 epilogue warps, the two warps of a quarter alternate 128-column groups
-    uint32_t acc_phase = 0;
-    uint32_t stage = 0, phase = 0;
-    const uint32_t idesc256 = make_idesc_bf16(128, 256), idesc128 = make_idesc_bf16(128, 128);
+    uint32_t acc_phase = 0, stage = 0, phase = 0;
     const bool atomics = p.use_atomics != 0;
     for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
       const GramUnit w = gram_decode_unit(p, u);
-      const bool diag = (w.I == w.J);
-      if (ew == 0) {
-        mbar_wait(bar_tempty, acc_phase ^ 1u, 200u);   // all four warps have drained the previous unit's accumulators
-        tc_fence_after_sync();
-        for (int kb = w.kb0; kb < w.kb1; ++kb) {
-          const uint32_t sA = stage;
-          mbar_wait(bar_full + 8 * sA, phase, 300u + sA);
-          uint32_t sB = sA, phaseB = phase;
-          if (!diag) {
-            sB = sA + 1;
-            if (sB == kGfStages) { sB = 0; phaseB ^= 1u; }
-            mbar_wait(bar_full + 8 * sB, phaseB, 310u + sB);
-          }
-          tc_fence_after_sync();
-          if (lane == 0) {
-            const uint32_t aI = smem_base + sA * kGfStageBytes;   // rows of block I
-            const uint32_t aJ = smem_base + sB * kGfStageBytes;   // rows of block J (== I on the diagonal)
-            const uint32_t acc = (kb > w.kb0) ? 1u : 0u;
-#pragma unroll
-            for (uint32_t ks = 0; ks < kTileK / kUmmaK; ++ks) {
-              if ((int)(kb * 64 + ks * 16) >= p.HW) break;        // K tail: whole k-steps past HW are skipped
-              const uint32_t koff = ks * 32u;
-              // acc0: I rows 0-127 x J rows 0-255
-              umma_bf16(tmem_base + 0u, make_smem_desc_sw128(aI + koff), make_smem_desc_sw128(aJ + koff), idesc256,
-                        acc | ks);
-              if (diag) {
-                // acc1: I rows 128-255 x I rows 128-255 (the lower-left 128x128 block is never computed)
-                umma_bf16(tmem_base + 256u, make_smem_desc_sw128(aI + 128u * kRowBytes + koff),
-                          make_smem_desc_sw128(aI + 128u * kRowBytes + koff), idesc128, acc | ks);
-              } else {
-                // acc1: I rows 128-255 x J rows 0-255
-                umma_bf16(tmem_base + 256u, make_smem_desc_sw128(aI + 128u * kRowBytes + koff),
-                          make_smem_desc_sw128(aJ + koff), idesc256, acc | ks);
-              }
-            }
-            umma_commit(bar_empty + 8 * sA);
-            if (!diag) umma_commit(bar_empty + 8 * sB);
-            if (kb + 1 == w.kb1) umma_commit(bar_tfull);
-          }
-          __syncwarp();
-          stage = sB + 1; phase = phaseB;
-          if (stage == kGfStages) { stage = 0; phase ^= 1u; }
-        }
-      }
+      if (ew == 0)
+        gf_issue_unit(p, w, smem_base, bar_full, bar_empty, bar_tfull, bar_tempty, tmem_base, stage, phase, acc_phase, lane);
       mbar_wait(bar_tfull, acc_phase, 400u);
       tc_fence_after_sync();
-      float* outp = p.out + (long long)w.b * p.out_img_stride;
-      const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-      for (int a = 0; a < 2; ++a) {
-        const int c_row = w.I * 256 + a * 128 + q * 32 + lane;
-        const int ncols = (a == 1 && diag) ? 128 : 256;
-        const int colbase = w.J * 256 + ((a == 1 && diag) ? 128 : 0);
-        if (w.I * 256 + a * 128 >= p.C) break;   // whole accumulator is padding (C <= 128)
-#pragma unroll 1
-        for (int g0 = hc * 128; g0 < ncols; g0 += 128 * (NEW / 4)) {
-          const int c_grp = colbase + g0;
-          if (c_grp >= p.C) break;              // padding columns
-          // a 128x128 block strictly above the diagonal is mirrored; diagonal blocks are complete on their own
-          const bool mirror = (c_grp >> 7) > (c_row >> 7);
-          if constexpr (KP >= 8) {
-            gram_epi_pool_group128<KP>(lane_addr + (uint32_t)(a * 256 + g0), c_row, c_grp, p.C, p.g, p.scale, outp, mirror,
-                                       atomics, lane);
-          } else {
-#pragma unroll 1
-            for (int n0 = 0; n0 < 128; n0 += 32) {
-              const int c_col0 = c_grp + n0;
-              if (c_col0 >= p.C) break;
-              float v[32];
-              tmem_ld32(lane_addr + (uint32_t)(a * 256 + g0 + n0), v);
-              if (KP > 0)
-                gram_epi_pool_chunk<(KP > 0 ? KP : 1)>(v, c_row, c_col0, p.C, p.g, p.scale, outp, mirror, atomics, lane);
-              else gram_epi_dense_chunk(v, c_row, c_col0, p.C, p.scale, outp, mirror, atomics);
-            }
-          }
-        }
-      }
+      gf_epilogue_unit<KP>(p, w, tmem_base, q, hc, NEW / 4, atomics, lane);
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty);

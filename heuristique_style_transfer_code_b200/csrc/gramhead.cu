@@ -3,6 +3,7 @@
 #include "../../include/gramhead.h"
 #include "common.cuh"
 #include "gram_fwd.cuh"
+#include "gram_fwd_tma.cuh"
 #include "gram_bwd.cuh"
 #include "gram_bwd2.cuh"
 #include "attn_head.cuh"
@@ -47,7 +48,7 @@ static int g_opt_fwd_producer_warps = 0;    // 0 = auto
 static int g_opt_fwd_epilogue_warps = 0;    // 0 = auto
 static int g_opt_bwd_variant = 2;   // 1 = transposed product (gram_bwd.cuh), 2 = MN-major F operand (gram_bwd2.cuh)
 static int g_opt_bwd_nhw = 0;       // 0 = auto, 128, 256
-static int g_opt_bwd_producer_warps = 16;   // NHW = 256 only
+static int g_opt_bwd_producer_warps = 8;    // NHW = 256 only; measured: 8 (separate MMA warp) beats 16 (merged) on every shape
 static int g_opt_attn_gemm = 1;     // 1 = tcgen05 split-bf16 GEMM for the attention linear layers, 0 = fp32 SIMT
 
 // D = A B (+ bias) with strided fp32 operands: tensor-core path when the layout allows it, fp32 FMA kernel otherwise.
@@ -74,10 +75,10 @@ static cudaError_t launch_gram_fwd_one(const GramFwdParams& p, int grid, cudaStr
 
 template <int SRC>
 static cudaError_t launch_gram_fwd_kp(const GramFwdParams& p, int kp, int grid, cudaStream_t st) {
-  // Warp mix (profiles/r01d: the C = 256 stage waits on HBM loads -> 16 producer warps; from C = 512 on the K loop is
-  // short and the TMEM drain + pooling bounds the unit time -> 8 epilogue warps). gh_set_option overrides.
+  // Warp mix: 16 producer + 4 epilogue warps measured best on every ResNet stage shape (profiles/r01e_kernel_timings.log);
+  // 8 epilogue warps (24 warps -> 80 registers/thread) spill in the producer loop and lose. gh_set_option overrides.
   const int npw = g_opt_fwd_producer_warps ? g_opt_fwd_producer_warps : 16;
-  const int nepi = g_opt_fwd_epilogue_warps ? g_opt_fwd_epilogue_warps : (p.C >= 512 ? 8 : 4);
+  const int nepi = g_opt_fwd_epilogue_warps ? g_opt_fwd_epilogue_warps : 4;
 #define GH_LAUNCH_GF(KP)                                                                  \
   {                                                                                       \
     if (npw == 8) return launch_gram_fwd_one<SRC, KP, 8, 4>(p, grid, st);                 \
@@ -94,6 +95,28 @@ static cudaError_t launch_gram_fwd_kp(const GramFwdParams& p, int kp, int grid, 
     default: return cudaErrorInvalidValue;
   }
 #undef GH_LAUNCH_GF
+}
+
+static int g_opt_fwd_tma = 1;       // bf16 features with TMA-legal pitches: cp.async.bulk.tensor producers
+
+template <int KP>
+static cudaError_t launch_gram_fwd_tma_one(const GramFwdParams& p, const CUtensorMap& map, int grid, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(gram_fwd_tma_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)kGfSmemBytes);
+  if (e != cudaSuccess) return e;
+  gram_fwd_tma_kernel<KP><<<grid, kGtThreads, kGfSmemBytes, st>>>(p, map);
+  return cudaGetLastError();
+}
+static cudaError_t launch_gram_fwd_tma(const GramFwdParams& p, const CUtensorMap& map, int kp, int grid, cudaStream_t st) {
+  switch (kp) {
+    case 0: return launch_gram_fwd_tma_one<0>(p, map, grid, st);
+    case 8: return launch_gram_fwd_tma_one<8>(p, map, grid, st);
+    case 16: return launch_gram_fwd_tma_one<16>(p, map, grid, st);
+    case 32: return launch_gram_fwd_tma_one<32>(p, map, grid, st);
+    case 64: return launch_gram_fwd_tma_one<64>(p, map, grid, st);
+    case 128: return launch_gram_fwd_tma_one<128>(p, map, grid, st);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 static int gram_fwd_common(const void* F, int f_dtype, long long img_stride, long long row_stride, int B, int C, int HW,
@@ -144,7 +167,10 @@ static int gram_fwd_common(const void* F, int f_dtype, long long img_stride, lon
     if (s4 && addr % 16 == 0) e = launch_gram_fwd_kp<0>(p, kp, grid, st);
     else e = launch_gram_fwd_kp<1>(p, kp, grid, st);
   } else {
-    if (s4 && addr % 8 == 0) e = launch_gram_fwd_kp<2>(p, kp, grid, st);
+    CUtensorMap map;
+    if (g_opt_fwd_tma && make_feature_tensor_map(&map, F, img_stride, row_stride, B, C, HW))
+      e = launch_gram_fwd_tma(p, map, kp, grid, st);
+    else if (s4 && addr % 8 == 0) e = launch_gram_fwd_kp<2>(p, kp, grid, st);
     else e = launch_gram_fwd_kp<3>(p, kp, grid, st);
   }
   return (int)e;
@@ -309,6 +335,11 @@ int gh_set_option(const char* name, int value) {
   if (key == "gram_fwd_producer_warps") {
     if (value != 0 && value != 8 && value != 16) return GH_ERR_BAD_ARG;
     g_opt_fwd_producer_warps = value;
+    return 0;
+  }
+  if (key == "gram_fwd_tma") {
+    if (value != 0 && value != 1) return GH_ERR_BAD_ARG;
+    g_opt_fwd_tma = value;
     return 0;
   }
   if (key == "gram_fwd_epilogue_warps") {

@@ -33,7 +33,8 @@ int gh_version(void);
 int gh_sm_count(void);
 
 /* Launch tuning, process-wide. Known names: "gram_fwd_producer_warps" (0 = auto, 8, 16) and
- * "gram_fwd_epilogue_warps" (0 = auto, 4, 8); "gram_bwd_variant"
+ * "gram_fwd_epilogue_warps" (0 = auto, 4, 8); "gram_fwd_tma" (1 = TMA-staged operands for bf16 features whose
+ * pitches are multiples of 16 B, 0 = always the ld.global producers; default 1); "gram_bwd_variant"
  * (1 = transposed product with gathered F^T tiles, 2 = F consumed as an MN-major operand, default 2); "gram_bwd_nhw"
  * (x-tile width of variant 2: 0 = auto, 128, 256); "gram_bwd_producer_warps" (8 or 16, for x-tile width 256); "attn_gemm" (1 = tcgen05 split-bf16 GEMMs for the attention linear
  * layers, 0 = fp32 FMA kernels; default 1). Unknown name or value outside the allowed set: GH_ERR_BAD_ARG. */

@@ -103,7 +103,7 @@ def test_gram_backward_variants_agree(ops):
     finally:
         _lib.lib().gh_set_option(b"gram_bwd_variant", 2)
         _lib.lib().gh_set_option(b"gram_bwd_nhw", 0)
-        _lib.lib().gh_set_option(b"gram_bwd_producer_warps", 16)
+        _lib.lib().gh_set_option(b"gram_bwd_producer_warps", 8)
 
 
 def test_producer_warp_variants_agree(ops):

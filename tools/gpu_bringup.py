@@ -335,7 +335,7 @@ def timing():
                   f"  {fl/ms/1e9:8.1f} TFLOP/s ({fl/ms/1e9/peaks['bf16_tflops']:.2f} of tensor)")
         _lib.lib().gh_set_option(b"gram_bwd_variant", 2)
         _lib.lib().gh_set_option(b"gram_bwd_nhw", 0)
-        _lib.lib().gh_set_option(b"gram_bwd_producer_warps", 16)
+        _lib.lib().gh_set_option(b"gram_bwd_producer_warps", 8)
         # torch reference ops on the same GPU (fp32 bmm + div + pool), for scale
         xf = x
         for _ in range(2):
