@@ -3,9 +3,10 @@
 #include "../../include/gramhead.h"
 #include "common.cuh"
 #include "gram_fwd.cuh"
-#include "gram_fwd_tma.cuh"
+#include "gram_fwd_pair.cuh"
 #include "gram_bwd.cuh"
 #include "gram_bwd2.cuh"
+#include "gram_bwd_pair.cuh"
 #include "attn_head.cuh"
 #include "umma_gemm.cuh"
 #include <string>
@@ -34,8 +35,15 @@ static int ilog2_exact(int v) {
 // K split of the Gram forward. Measured on B200 (profiles/r01*_kernel_timings.log): once there is at least one unit
 // per CTA, splitting K only adds atomics and epilogues (C=512: 151 us unsplit vs 179 us split in two), so K is split
 // only to fill the machine at small batch (camera mode: 1 image -> 1..10 units), keeping >= 2 k-blocks per part.
-static int choose_ksplit(long long base_units, int nkb, int ctas) {
-  if (base_units >= ctas) return 1;
+static int choose_ksplit(long long base_units, int nkb, int ctas, bool balance = false) {
+  if (base_units >= ctas) {
+    if (!balance) return 1;   // single-CTA kernel: its epilogue is not overlapped, a second one per unit costs more than it evens out
+    // Whole units per worker leave the last round partly empty (256 images on 74 CTA pairs: 4 rounds for 3.46 rounds
+    // of work). Two K halves per unit even that out, and two partial sums meeting in a zeroed fp32 slot add to the
+    // same bits in either order, so the result stays deterministic.
+    const long long r1 = (base_units + ctas - 1) / ctas * 2, r2 = (2 * base_units + ctas - 1) / ctas;
+    return (nkb >= 8 && r2 * 100 <= r1 * 93) ? 2 : 1;
+  }
   long long ks = (2LL * ctas + base_units - 1) / base_units;
   const int kmax = nkb / 2 > 1 ? nkb / 2 : 1;
   if (ks > kmax) ks = kmax;
@@ -97,24 +105,28 @@ static cudaError_t launch_gram_fwd_kp(const GramFwdParams& p, int kp, int grid, 
 #undef GH_LAUNCH_GF
 }
 
-static int g_opt_fwd_tma = 1;       // bf16 features with TMA-legal pitches: cp.async.bulk.tensor producers
+// Pair (cta_group::2, TMA-staged) kernels. -1 = auto, 0 = never, 1 = whenever TMA can describe the tensors.
+static int g_opt_fwd_pair = -1;
+static int g_opt_bwd_pair = -1;
+static int g_opt_tma_f32_type = 1;  // tensor-map data type for fp32 features: 0 = FLOAT32, 1 = TFLOAT32
 
-template <int KP>
-static cudaError_t launch_gram_fwd_tma_one(const GramFwdParams& p, const CUtensorMap& map, int grid, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(gram_fwd_tma_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)kGfSmemBytes);
+template <int KIND, int KP>
+static cudaError_t launch_gram_fwd_pair_one(const GramFwdParams& p, const CUtensorMap& map, int npairs, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(gram_fwd_pair_kernel<KIND, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)kFpSmemBytes);
   if (e != cudaSuccess) return e;
-  gram_fwd_tma_kernel<KP><<<grid, kGtThreads, kGfSmemBytes, st>>>(p, map);
+  gram_fwd_pair_kernel<KIND, KP><<<2 * npairs, kFpThreads, kFpSmemBytes, st>>>(p, map);
   return cudaGetLastError();
 }
-static cudaError_t launch_gram_fwd_tma(const GramFwdParams& p, const CUtensorMap& map, int kp, int grid, cudaStream_t st) {
+template <int KIND>
+static cudaError_t launch_gram_fwd_pair(const GramFwdParams& p, const CUtensorMap& map, int kp, int npairs, cudaStream_t st) {
   switch (kp) {
-    case 0: return launch_gram_fwd_tma_one<0>(p, map, grid, st);
-    case 8: return launch_gram_fwd_tma_one<8>(p, map, grid, st);
-    case 16: return launch_gram_fwd_tma_one<16>(p, map, grid, st);
-    case 32: return launch_gram_fwd_tma_one<32>(p, map, grid, st);
-    case 64: return launch_gram_fwd_tma_one<64>(p, map, grid, st);
-    case 128: return launch_gram_fwd_tma_one<128>(p, map, grid, st);
+    case 0: return launch_gram_fwd_pair_one<KIND, 0>(p, map, npairs, st);
+    case 8: return launch_gram_fwd_pair_one<KIND, 8>(p, map, npairs, st);
+    case 16: return launch_gram_fwd_pair_one<KIND, 16>(p, map, npairs, st);
+    case 32: return launch_gram_fwd_pair_one<KIND, 32>(p, map, npairs, st);
+    case 64: return launch_gram_fwd_pair_one<KIND, 64>(p, map, npairs, st);
+    case 128: return launch_gram_fwd_pair_one<KIND, 128>(p, map, npairs, st);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -139,6 +151,7 @@ static int gram_fwd_common(const void* F, int f_dtype, long long img_stride, lon
   const int sms = sm_count_cached();
   const int ctas = (max_ctas > 0 && max_ctas < sms) ? max_ctas : sms;
   const long long base_units = (long long)B * p.nST;
+  const int ksplit_arg = ksplit;
   if (ksplit <= 0) ksplit = choose_ksplit(base_units, p.nkb, ctas);
   if (ksplit > p.nkb) ksplit = p.nkb;
   p.ksplit = ksplit;
@@ -147,6 +160,38 @@ static int gram_fwd_common(const void* F, int f_dtype, long long img_stride, lon
   p.total_units = (int)total;
   p.g = g; p.out = out; p.out_img_stride = out_img_stride;
   p.scale = (mode == GRAM_POOL) ? 1.0f / ((float)HW * (float)kp * (float)kp) : 1.0f / (float)HW;
+
+  // ---- CTA-pair kernel with TMA-staged operands (bf16 -> kind::f16, fp32 -> kind::tf32) ----
+  const bool is_bf16 = (f_dtype == GH_DTYPE_BF16);
+  const bool want_pair = g_opt_fwd_pair == 1 || (g_opt_fwd_pair == -1 && (is_bf16 || C >= 512));
+  if (want_pair && sms >= 2) {
+    CUtensorMap map;
+    const int kb_elems = is_bf16 ? 64 : 32;
+    if (make_tensor_map_xcb(&map, F, is_bf16, img_stride, row_stride, B, C, HW, kb_elems, 128, g_opt_tma_f32_type)) {
+      GramFwdParams q = p;
+      q.nkb = (HW + kb_elems - 1) / kb_elems;
+      int npairs = ctas / 2;
+      if (npairs < 1) npairs = 1;
+      int ks = ksplit_arg > 0 ? ksplit_arg : choose_ksplit(base_units, q.nkb, npairs, /*balance=*/true);
+      if (ks > q.nkb) ks = q.nkb;
+      q.ksplit = ks;
+      const long long tot = base_units * ks;
+      if (tot <= 0x7fffffffLL) {
+        q.total_units = (int)tot;
+        q.use_atomics = (ks > 1 || kp > 32) ? 1 : 0;
+        cudaError_t e2 = cudaSuccess;
+        if (q.use_atomics) {
+          if (mode == GRAM_POOL) e2 = cudaMemset2DAsync(out, (size_t)out_img_stride * 4, 0, (size_t)g * g * 4, (size_t)B, st);
+          else e2 = cudaMemsetAsync(out, 0, (size_t)B * C * C * 4, st);
+          if (e2 != cudaSuccess) return (int)e2;
+        }
+        if (tot < npairs) npairs = (int)tot;
+        e2 = is_bf16 ? launch_gram_fwd_pair<KIND_BF16>(q, map, kp, npairs, st)
+                     : launch_gram_fwd_pair<KIND_TF32>(q, map, kp, npairs, st);
+        return (int)e2;
+      }
+    }
+  }
   // every output element has exactly one writer unless K is split or a pooled row spans two epilogue warps (k > 32)
   p.use_atomics = (ksplit > 1 || kp > 32) ? 1 : 0;
 
@@ -167,10 +212,7 @@ static int gram_fwd_common(const void* F, int f_dtype, long long img_stride, lon
     if (s4 && addr % 16 == 0) e = launch_gram_fwd_kp<0>(p, kp, grid, st);
     else e = launch_gram_fwd_kp<1>(p, kp, grid, st);
   } else {
-    CUtensorMap map;
-    if (g_opt_fwd_tma && make_feature_tensor_map(&map, F, img_stride, row_stride, B, C, HW))
-      e = launch_gram_fwd_tma(p, map, kp, grid, st);
-    else if (s4 && addr % 8 == 0) e = launch_gram_fwd_kp<2>(p, kp, grid, st);
+    if (s4 && addr % 8 == 0) e = launch_gram_fwd_kp<2>(p, kp, grid, st);
     else e = launch_gram_fwd_kp<3>(p, kp, grid, st);
   }
   return (int)e;
@@ -196,6 +238,49 @@ static int gram_bwd_common(const void* F, int f_dtype, long long img_stride, lon
   } else {
     if (!dG) return GH_ERR_BAD_ARG;
     p.scale = 1.0f / (float)HW;
+  }
+  // ---- CTA-pair kernel: F TMA-staged as the MN-major operand, dF written with TMA stores ----
+  {
+    const bool is_bf16 = (f_dtype == GH_DTYPE_BF16);
+    const int sms_p = sm_count_cached();
+    const int ctas_p = (max_ctas > 0 && max_ctas < sms_p) ? max_ctas : sms_p;
+    // POOL: a 16 B chunk of the generated A tile must lie inside one pooled column (k >= 8 covers bf16 and tf32)
+    const bool want_pair = g_opt_bwd_pair != 0 && ctas_p >= 2 && (mode != GRAM_POOL || (g <= kBpMaxG && (C / g) >= 8));
+    CUtensorMap tmF, tmD;
+    const int kc_elems = is_bf16 ? 64 : 32;
+    if (want_pair &&
+        make_tensor_map_xcb(&tmF, F, is_bf16, img_stride, row_stride, B, C, HW, kc_elems, kc_elems, g_opt_tma_f32_type,
+                            /*atom32=*/!is_bf16) &&
+        make_tensor_map_xcb(&tmD, dF, false, df_img_stride, df_row_stride, B, C, HW, 32, 32, 0)) {
+      GramBwdPairParams q;
+      q.B = B; q.C = C; q.HW = HW; q.mode = mode;
+      q.dP = dP; q.dp_img_stride = dp_img_stride; q.g = g; q.kshift = p.kshift; q.dG = dG;
+      q.scale = p.scale;
+      gbp_plan_tiles(HW, &q.NT, &q.nHT);
+      q.nCB = (C + 255) / 256;
+      q.nkc = (C + kc_elems - 1) / kc_elems;
+      const long long tot = (long long)B * q.nHT * q.nCB;
+      if (tot <= 0x7fffffffLL) {
+        q.total_units = (int)tot;
+        int npairs = ctas_p / 2;
+        if (tot < npairs) npairs = (int)tot;
+        cudaError_t e3 = cudaErrorInvalidValue;
+#define GH_LAUNCH_BP(KIND, MODE)                                                                                       \
+        {                                                                                                              \
+          e3 = cudaFuncSetAttribute(gram_bwd_pair_kernel<KIND, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                    (int)kBpSmemBytes);                                                                \
+          if (e3 != cudaSuccess) return (int)e3;                                                                       \
+          gram_bwd_pair_kernel<KIND, MODE><<<2 * npairs, kBpThreads, kBpSmemBytes, st>>>(q, tmF, tmD);                 \
+        }
+        if (is_bf16) {
+          if (mode == GRAM_POOL) GH_LAUNCH_BP(KIND_BF16, GRAM_POOL) else GH_LAUNCH_BP(KIND_BF16, GRAM_DENSE)
+        } else {
+          if (mode == GRAM_POOL) GH_LAUNCH_BP(KIND_TF32, GRAM_POOL) else GH_LAUNCH_BP(KIND_TF32, GRAM_DENSE)
+        }
+#undef GH_LAUNCH_BP
+        return (int)cudaGetLastError();
+      }
+    }
   }
   if (g_opt_bwd_variant == 2) {
     GramBwd2Params q;
@@ -337,9 +422,19 @@ int gh_set_option(const char* name, int value) {
     g_opt_fwd_producer_warps = value;
     return 0;
   }
-  if (key == "gram_fwd_tma") {
+  if (key == "gram_fwd_pair") {
+    if (value < -1 || value > 1) return GH_ERR_BAD_ARG;
+    g_opt_fwd_pair = value;
+    return 0;
+  }
+  if (key == "gram_bwd_pair") {
+    if (value < -1 || value > 1) return GH_ERR_BAD_ARG;
+    g_opt_bwd_pair = value;
+    return 0;
+  }
+  if (key == "tma_f32_type") {
     if (value != 0 && value != 1) return GH_ERR_BAD_ARG;
-    g_opt_fwd_tma = value;
+    g_opt_tma_f32_type = value;
     return 0;
   }
   if (key == "gram_fwd_epilogue_warps") {

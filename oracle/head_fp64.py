@@ -34,6 +34,22 @@ def bf16_round(x: np.ndarray) -> np.ndarray:
     return a.astype(np.uint32).view(np.float32).reshape(np.shape(x))
 
 
+def tf32_trunc(x: np.ndarray) -> np.ndarray:
+    """fp32 with the low 13 mantissa bits dropped: what a tensor core reading fp32 words as kind::tf32 operands sees."""
+    a = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32) & np.uint32(0xFFFFE000)
+    return a.view(np.float32).reshape(np.shape(x))
+
+
+def tf32_round(x: np.ndarray) -> np.ndarray:
+    """fp32 rounded to the nearest tf32 (ties away from zero), as cvt.rna.tf32.f32 does."""
+    a = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    a = (a + 0x1000) & 0xFFFFE000
+    return a.astype(np.uint32).view(np.float32).reshape(np.shape(x))
+
+
+_OPERAND_ROUNDING = {"bf16": bf16_round, "tf32_trunc": tf32_trunc, "tf32_round": tf32_round}
+
+
 def gram(features: np.ndarray) -> np.ndarray:
     """(B, C, H, W) or (B, C, HW) -> (B, C, C): F F^T / HW."""
     f = np.asarray(features, dtype=np.float64)
@@ -64,12 +80,13 @@ def adaptive_pool(gmat: np.ndarray, g: int) -> np.ndarray:
 
 
 def descriptors(features: Sequence[np.ndarray], g: int, operand_rounding: Optional[str] = None) -> np.ndarray:
-    """List of L stage feature maps -> (B, L, g*g). operand_rounding='bf16' rounds the Gram operands first."""
+    """List of L stage feature maps -> (B, L, g*g). operand_rounding in {'bf16', 'tf32_trunc', 'tf32_round'} applies
+    that operand model to the Gram operands first (see _OPERAND_ROUNDING)."""
     out = []
     for f in features:
         f = np.asarray(f)
-        if operand_rounding == "bf16":
-            f = bf16_round(f.astype(np.float32))
+        if operand_rounding is not None:
+            f = _OPERAND_ROUNDING[operand_rounding](f.astype(np.float32))
         p = adaptive_pool(gram(f), g)
         out.append(p.reshape(p.shape[0], g * g))
     return np.stack(out, axis=1)

@@ -1,11 +1,18 @@
 """Parity of the sm_100a kernels against the oracle, through the C ABI (ops.py is a thin ctypes layer over it).
 
+Two kernel families sit behind every Gram entry point and both are tested explicitly (`path`):
+  * "ldg"  - single-CTA kernels whose producer warps convert fp32 -> bf16 (round to nearest even) on the way to smem;
+  * "pair" - CTA-pair (cta_group::2) kernels with TMA-staged operands: bf16 features feed kind::f16 as they are,
+             fp32 features feed kind::tf32, rounded to the nearest tf32 by the TMA unit (TFLOAT32 tensor maps);
+  * "auto" - whatever the library picks for the shape (the shipped default).
+
 Tolerances (written next to each assert):
-  * Gram / descriptor vs the fp64 oracle on fp32 inputs:            normwise rel. err <= 1e-3  (task statement; bf16
-    operands, fp32 accumulation) -- measured 2e-5 .. 3e-4
-  * same vs the fp64 oracle fed bf16-rounded operands:               <= 1e-5  (only fp32 accumulation order differs)
-  * attention head fwd/bwd (fp32 FMA kernels) vs fp64 oracle:        <= 2e-5
-  * Gram backward (bf16 operands incl. the bf16-rounded gradient):   <= 6e-3 normwise
+  * Gram / descriptor vs the fp64 oracle on fp32 inputs:            normwise rel. err <= 1e-3  (task statement)
+                                                                     -- measured 2e-5 .. 3e-4 (bf16), 4e-6 .. 9e-5 (tf32)
+  * same vs the fp64 oracle fed the path's operand model:            <= 1e-5  (only fp32 accumulation order differs)
+  * attention head fwd/bwd vs fp64 oracle:                           <= 2e-5
+  * Gram backward: bf16 operands incl. the bf16-rounded gradient     <= 6e-3 normwise (measured 1.4e-3 .. 2.4e-3);
+                   tf32 operands (pair path on fp32 features)        <= 1e-3 (measured 2.2e-4 .. 2.8e-4)
 """
 import numpy as np
 import pytest
@@ -31,6 +38,38 @@ def npf(t):
     return t.detach().float().cpu().numpy()
 
 
+PATHS = ("ldg", "pair", "auto")
+
+
+class kernel_path:
+    """Context manager: force one kernel family for the forward and backward Gram entry points."""
+
+    def __init__(self, path):
+        self.value = {"ldg": 0, "pair": 1, "auto": -1}[path]
+
+    def __enter__(self):
+        from heuristique_style_transfer_code_b200 import _lib
+        assert _lib.lib().gh_set_option(b"gram_fwd_pair", self.value) == 0
+        assert _lib.lib().gh_set_option(b"gram_bwd_pair", self.value) == 0
+        return self
+
+    def __exit__(self, *exc):
+        from heuristique_style_transfer_code_b200 import _lib
+        _lib.lib().gh_set_option(b"gram_fwd_pair", -1)
+        _lib.lib().gh_set_option(b"gram_bwd_pair", -1)
+        return False
+
+
+def operand_model_err(got, ref_fn, xf, path, dtype):
+    """Error of `got` against the fp64 oracle fed the operand model of the kernel family that ran.
+    ref_fn(rounded_features) -> reference. bf16 features are exact in every family."""
+    if dtype == "bf16":
+        return O.rel_err(got, ref_fn(xf))
+    models = {"ldg": (O.bf16_round,), "pair": (O.tf32_round, O.bf16_round), "auto": (O.tf32_round, O.bf16_round)}[path]
+    # "pair" falls back to the ldg kernels where TMA cannot describe the tensor (e.g. HW = 49: 196 B pitch)
+    return min(O.rel_err(got, ref_fn(m(xf))) for m in models)
+
+
 def test_cuda_is_present():
     assert torch.cuda.is_available(), "pytest -m gpu must run on a CUDA machine"
     assert torch.cuda.get_device_capability()[0] == 10, "kernels are built for sm_100a only"
@@ -45,13 +84,17 @@ def test_cuda_is_present():
     (5, 256, 3136, 32, 0, "f32"),          # auto K split
     (5, 256, 3136, 32, 4, "f32"),          # K split, fp32 atomics
     (2, 256, 3136, 32, 1, "bf16"),         # bf16 features
+    (3, 512, 784, 32, 1, "bf16"),          # bf16, off-diagonal super-tiles
+    (2, 1024, 200, 32, 0, "bf16"),         # bf16, K tail inside a TMA box
+    (2, 384, 200, 48, 1, "f32"),           # C not a multiple of 256: padded rows / columns
     (2, 256, 12544, 32, 0, "f32"),         # layer1 @448 (camera config)
     (2, 1024, 196, 8, 1, "f32"),           # k = 128
     (2, 64, 3136, 8, 1, "f32"),            # C < 128: second accumulator is all padding
     (300, 256, 256, 32, 1, "f32"),         # more units than CTAs: persistent loop, ring wrap
     (1, 256, 3136, 32, 0, "f32"),          # batch 1 (camera): K split fills the SMs
 ])
-def test_pooled_gram_forward(ops, B, C, HW, g, ksplit, dtype):
+@pytest.mark.parametrize("path", PATHS)
+def test_pooled_gram_forward(ops, B, C, HW, g, ksplit, dtype, path):
     torch.manual_seed(0)
     x = torch.relu(torch.randn(B, C, HW, device="cuda"))
     if dtype == "bf16":
@@ -59,7 +102,8 @@ def test_pooled_gram_forward(ops, B, C, HW, g, ksplit, dtype):
     desc = torch.full((B, 2, g * g), float("nan"), device="cuda")
     ops.KSPLIT = ksplit
     try:
-        ops.gram_pool_fwd_(x, g, desc, 1)
+        with kernel_path(path):
+            ops.gram_pool_fwd_(x, g, desc, 1)
     finally:
         ops.KSPLIT = 0
     torch.cuda.synchronize()
@@ -67,7 +111,7 @@ def test_pooled_gram_forward(ops, B, C, HW, g, ksplit, dtype):
     xf = npf(x)
     assert torch.isnan(desc[:, 0]).all(), "the other stage's slice must not be touched"
     assert O.rel_err(got, O.descriptors([xf], g)[:, 0]) <= 1e-3
-    assert O.rel_err(got, O.descriptors([xf], g, operand_rounding="bf16")[:, 0]) <= 1e-5
+    assert operand_model_err(got, lambda f: O.descriptors([f], g)[:, 0], xf, path, dtype) <= 1e-5
     sym = got.reshape(B, g, g)
     assert np.abs(sym - sym.transpose(0, 2, 1)).max() <= 1e-5 * np.abs(sym).max()
 
@@ -93,6 +137,7 @@ def test_gram_backward_variants_agree(ops):
     dd = torch.randn(3, 1, 1024, device="cuda")
     ref = O.gram_pool_backward(npf(x), 32, npf(dd[:, 0]))
     try:
+        _lib.lib().gh_set_option(b"gram_bwd_pair", 0)
         for variant, nhw, npw in [(1, 0, 16), (2, 128, 8), (2, 256, 8), (2, 256, 16)]:
             lib = _lib.lib()
             assert lib.gh_set_option(b"gram_bwd_variant", variant) == 0
@@ -104,6 +149,7 @@ def test_gram_backward_variants_agree(ops):
         _lib.lib().gh_set_option(b"gram_bwd_variant", 2)
         _lib.lib().gh_set_option(b"gram_bwd_nhw", 0)
         _lib.lib().gh_set_option(b"gram_bwd_producer_warps", 8)
+        _lib.lib().gh_set_option(b"gram_bwd_pair", -1)
 
 
 def test_producer_warp_variants_agree(ops):
@@ -116,7 +162,8 @@ def test_producer_warp_variants_agree(ops):
         assert _lib.lib().gh_set_option(b"gram_fwd_epilogue_warps", nepi) == 0
         desc = torch.empty((4, 1, 1024), device="cuda")
         ops.KSPLIT = 1
-        ops.gram_pool_fwd_(x, 32, desc, 0)
+        with kernel_path("ldg"):
+            ops.gram_pool_fwd_(x, 32, desc, 0)
         ops.KSPLIT = 0
         outs.append(desc.clone())
     _lib.lib().gh_set_option(b"gram_fwd_producer_warps", 0)
@@ -126,42 +173,56 @@ def test_producer_warp_variants_agree(ops):
 
 @pytest.mark.parametrize("B,C,HW,ksplit", [(1, 64, 3136, 1), (2, 256, 784, 1), (2, 512, 196, 1), (1, 64, 3136, 0),
                                            (2, 320, 100, 1), (1, 256, 196, 1)])
-def test_dense_gram_forward(ops, B, C, HW, ksplit):
+@pytest.mark.parametrize("path", PATHS)
+def test_dense_gram_forward(ops, B, C, HW, ksplit, path):
     torch.manual_seed(0)
     x = torch.relu(torch.randn(B, C, HW, device="cuda"))
     ops.KSPLIT = ksplit
     try:
-        G = ops.gram_dense_fwd(x)
+        with kernel_path(path):
+            G = ops.gram_dense_fwd(x)
     finally:
         ops.KSPLIT = 0
     torch.cuda.synchronize()
     assert O.rel_err(npf(G), O.gram(npf(x))) <= 1e-3
-    assert O.rel_err(npf(G), O.gram(O.bf16_round(npf(x)))) <= 1e-5
+    assert operand_model_err(npf(G), O.gram, npf(x), path, "f32") <= 1e-5
     assert float((G - G.transpose(1, 2)).abs().max()) <= 1e-6 * float(G.abs().max())
 
 
 @pytest.mark.parametrize("B,C,HW,g,dtype", [(1, 256, 128, 32, "f32"), (2, 256, 3136, 32, "f32"), (2, 512, 784, 32, "f32"),
                                             (2, 1024, 196, 32, "f32"), (2, 2048, 49, 32, "f32"),
-                                            (2, 256, 3136, 32, "bf16"), (40, 256, 784, 32, "f32"), (2, 64, 100, 16, "f32")])
-def test_pooled_gram_backward(ops, B, C, HW, g, dtype):
+                                            (2, 256, 3136, 32, "bf16"), (40, 256, 784, 32, "f32"), (2, 64, 100, 16, "f32"),
+                                            (2, 1024, 200, 32, "bf16"), (2, 384, 200, 48, "f32"), (2, 64, 100, 8, "f32"),
+                                            (1, 256, 12544, 32, "f32")])
+@pytest.mark.parametrize("path", PATHS)
+def test_pooled_gram_backward(ops, B, C, HW, g, dtype, path):
     torch.manual_seed(0)
     x = torch.relu(torch.randn(B, C, HW, device="cuda"))
     if dtype == "bf16":
         x = x.bfloat16()
     dd = torch.randn(B, 2, g * g, device="cuda")
-    df = ops.gram_pool_bwd(x, g, dd, 1)
+    with kernel_path(path):
+        df = ops.gram_pool_bwd(x, g, dd, 1)
     torch.cuda.synchronize()
-    assert O.rel_err(npf(df), O.gram_pool_backward(npf(x), g, npf(dd[:, 1]))) <= 6e-3
+    err = O.rel_err(npf(df), O.gram_pool_backward(npf(x), g, npf(dd[:, 1])))
+    assert err <= 6e-3
+    # fp32 features on the pair kernels are tf32 operands (the generated gradient tile included): 10x tighter.
+    # (HW = 49 has a 196 B pitch TMA cannot describe: that shape stays on the ldg kernels in every mode.)
+    if path != "ldg" and dtype == "f32" and (HW * 4) % 16 == 0:
+        assert err <= 1e-3
 
 
 @pytest.mark.parametrize("B,C,HW", [(1, 64, 3136), (2, 256, 196), (1, 512, 100)])
-def test_dense_gram_backward(ops, B, C, HW):
+@pytest.mark.parametrize("path", PATHS)
+def test_dense_gram_backward(ops, B, C, HW, path):
     torch.manual_seed(0)
     x = torch.relu(torch.randn(B, C, HW, device="cuda"))
     dg = torch.randn(B, C, C, device="cuda")
-    df = ops.gram_dense_bwd(x, dg)
+    with kernel_path(path):
+        df = ops.gram_dense_bwd(x, dg)
     torch.cuda.synchronize()
-    assert O.rel_err(npf(df), O.gram_dense_backward(npf(x), npf(dg))) <= 6e-3
+    err = O.rel_err(npf(df), O.gram_dense_backward(npf(x), npf(dg)))
+    assert err <= (6e-3 if path == "ldg" else 1e-3)
 
 
 @pytest.mark.parametrize("B,C,HW,g", [(2, 256, 196, 24), (2, 64, 100, 7), (2, 256, 100, 64), (2, 64, 3136, 32)])
@@ -236,8 +297,18 @@ def test_golden_resnet_descriptors(ops, golden_resnet):
 
 
 # ---- size-independent properties at BASELINE.json's full sizes -------------------------------------------------------
+def _tf32_round_t(x):
+    return ((x.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+@pytest.mark.parametrize("path", ("ldg", "pair"))
 @pytest.mark.parametrize("C,HW", [(256, 3136), (512, 784), (1024, 196)])
-def test_full_size_properties(ops, C, HW):
+def test_full_size_properties(ops, C, HW, path):
+    with kernel_path(path):
+        _full_size_properties(ops, C, HW, path)
+
+
+def _full_size_properties(ops, C, HW, path):
     B, g = 256, 32
     torch.manual_seed(0)
     x = torch.relu(torch.randn(B, C, HW, device="cuda"))
@@ -258,7 +329,7 @@ def test_full_size_properties(ops, C, HW):
     assert float((desc - base).norm() / base.norm()) <= 1e-5
     # (4) trace identity: sum of the pooled diagonal * k  ==  mean_c of ||F_c||^2 / HW  summed ... checked in fp64 on a slice
     k = C // g
-    xs = x[:8].bfloat16().double()
+    xs = (x[:8].bfloat16() if path == "ldg" else _tf32_round_t(x[:8])).double()   # the family's operand model
     tr = (xs * xs).sum(dim=(1, 2)) / HW
     diag_blocks = base[:8, 0].double().view(8, g, g)
     # sum over all pooled entries * k^2 = sum_cd G[c][d] = ||sum_c F_c||^2 / HW

@@ -376,6 +376,213 @@ def timing():
     return True
 
 
+def _opt(name, value):
+    from heuristique_style_transfer_code_b200 import _lib
+    rc = _lib.lib().gh_set_option(name.encode(), value)
+    assert rc == 0, (name, value, rc)
+
+
+def _pair_fwd_case(B, C, HW, g, dtype="f32", ksplit=0, f32_type=0, relu=True):
+    import torch
+    from heuristique_style_transfer_code_b200 import ops
+    from oracle import head_fp64 as O
+    torch.manual_seed(0)
+    x = torch.randn(B, C, HW, device="cuda")
+    if relu:
+        x = torch.relu(x)
+    if dtype == "bf16":
+        x = x.bfloat16()
+    _opt("gram_fwd_pair", 1)
+    _opt("tma_f32_type", f32_type)
+    desc = torch.full((B, 2, g * g), float("nan"), device="cuda")
+    ops.KSPLIT = ksplit
+    ops.gram_pool_fwd_(x, g, desc, 1)
+    torch.cuda.synchronize()
+    ops.KSPLIT = 0
+    got = _np(desc[:, 1])
+    xf = _np(x)
+    errs = {"exact": O.rel_err(got, O.descriptors([xf], g)[:, 0])}
+    for model in (("bf16",) if dtype == "bf16" else ("tf32_trunc", "tf32_round", "bf16")):
+        errs[model] = O.rel_err(got, O.descriptors([xf], g, operand_rounding=model)[:, 0])
+    untouched = bool(torch.isnan(desc[:, 0]).all())
+    best = min(v for k, v in errs.items() if k != "exact") if dtype != "bf16" else errs["exact"]
+    print(f"pair-fwd B={B} C={C} HW={HW} g={g} {dtype} ksplit={ksplit} f32_type={f32_type}: " +
+          " ".join(f"{k}={v:.2e}" for k, v in errs.items()) + f" other-slice-untouched={untouched}", flush=True)
+    return errs["exact"] < 1e-3 and best < 2e-5 and untouched
+
+
+@case
+def pair_fwd_min():
+    ok = _pair_fwd_case(1, 256, 64, 32)
+    ok &= _pair_fwd_case(1, 256, 64, 32, dtype="bf16")
+    return ok
+
+
+@case
+def pair_fwd():
+    ok = True
+    for f32_type in (0, 1):
+        ok &= _pair_fwd_case(2, 256, 3136, 32, f32_type=f32_type)
+        ok &= _pair_fwd_case(3, 512, 784, 32, f32_type=f32_type)
+        ok &= _pair_fwd_case(2, 1024, 196, 32, f32_type=f32_type)
+    ok &= _pair_fwd_case(2, 256, 3136, 32, dtype="bf16")
+    ok &= _pair_fwd_case(3, 512, 784, 32, dtype="bf16")
+    ok &= _pair_fwd_case(2, 1024, 200, 32, dtype="bf16")
+    ok &= _pair_fwd_case(5, 256, 3136, 32, ksplit=4)
+    ok &= _pair_fwd_case(3, 512, 784, 32, ksplit=3, dtype="bf16")
+    ok &= _pair_fwd_case(2, 64, 100, 8)
+    ok &= _pair_fwd_case(2, 384, 200, 48)
+    ok &= _pair_fwd_case(2, 1024, 196, 8)              # k = 128: rows of a pooled bin span warps -> atomics
+    ok &= _pair_fwd_case(2, 2048, 64, 32)              # k = 64
+    ok &= _pair_fwd_case(300, 256, 256, 32)            # more units than pairs (persistent loop, phase wrap)
+    ok &= _pair_fwd_case(1, 256, 12544, 32)            # one image: K split across the machine
+    return ok
+
+
+@case
+def pair_fwd_dense():
+    import torch
+    from heuristique_style_transfer_code_b200 import ops
+    from oracle import head_fp64 as O
+    ok = True
+    _opt("gram_fwd_pair", 1)
+    for (B, C, HW, ks, dt) in [(1, 64, 3136, 1, "f32"), (2, 256, 784, 1, "f32"), (2, 512, 196, 1, "f32"), (1, 64, 3136, 0, "f32"),
+                               (2, 320, 100, 1, "f32"), (2, 512, 200, 1, "bf16")]:
+        torch.manual_seed(0)
+        x = torch.relu(torch.randn(B, C, HW, device="cuda"))
+        if dt == "bf16":
+            x = x.bfloat16()
+        ops.KSPLIT = ks
+        G = ops.gram_dense_fwd(x)
+        torch.cuda.synchronize()
+        ops.KSPLIT = 0
+        xf = _np(x)
+        e0 = O.rel_err(_np(G), O.gram(xf))
+        e1 = O.rel_err(_np(G), O.gram(O.tf32_trunc(xf)))
+        sym = float((G - G.transpose(1, 2)).abs().max())
+        print(f"pair-dense B={B} C={C} HW={HW} ksplit={ks} {dt}: rel_err vs fp64={e0:.3e} vs tf32-trunc fp64={e1:.3e} max|G-G^T|={sym:.3e}", flush=True)
+        ok &= e0 < 1e-3 and (sym == 0.0 or ks != 1)
+    return ok
+
+
+def _pair_bwd_case(B, C, HW, g, dtype="f32", f32_type=0):
+    import torch
+    from heuristique_style_transfer_code_b200 import ops
+    from oracle import head_fp64 as O
+    torch.manual_seed(0)
+    x = torch.relu(torch.randn(B, C, HW, device="cuda"))
+    if dtype == "bf16":
+        x = x.bfloat16()
+    dd = torch.randn(B, 2, g * g, device="cuda")
+    _opt("gram_bwd_pair", 1)
+    _opt("tma_f32_type", f32_type)
+    df = ops.gram_pool_bwd(x, g, dd, 1)
+    torch.cuda.synchronize()
+    xf = _np(x)
+    e0 = O.rel_err(_np(df), O.gram_pool_backward(xf, g, _np(dd[:, 1])))
+    e1 = O.rel_err(_np(df), O.gram_pool_backward(O.tf32_trunc(xf), g, _np(dd[:, 1])))
+    _opt("gram_bwd_pair", 0)
+    df_old = ops.gram_pool_bwd(x, g, dd, 1)
+    torch.cuda.synchronize()
+    e2 = O.rel_err(_np(df), _np(df_old))
+    print(f"pair-bwd B={B} C={C} HW={HW} g={g} {dtype} f32_type={f32_type}: rel_err vs fp64={e0:.3e} vs tf32-trunc-F fp64={e1:.3e} vs legacy kernel={e2:.3e}", flush=True)
+    return e0 < 3e-3
+
+
+@case
+def pair_bwd_min():
+    ok = _pair_bwd_case(1, 256, 128, 32)
+    ok &= _pair_bwd_case(1, 256, 128, 32, dtype="bf16")
+    return ok
+
+
+@case
+def pair_bwd():
+    ok = True
+    for f32_type in (0, 1):
+        ok &= _pair_bwd_case(2, 256, 3136, 32, f32_type=f32_type)
+        ok &= _pair_bwd_case(2, 512, 784, 32, f32_type=f32_type)
+        ok &= _pair_bwd_case(2, 1024, 196, 32, f32_type=f32_type)
+    ok &= _pair_bwd_case(2, 256, 3136, 32, dtype="bf16")
+    ok &= _pair_bwd_case(2, 1024, 200, 32, dtype="bf16")
+    ok &= _pair_bwd_case(40, 256, 784, 32)
+    ok &= _pair_bwd_case(2, 64, 100, 8)
+    ok &= _pair_bwd_case(2, 384, 200, 48)
+    ok &= _pair_bwd_case(2, 2048, 64, 32)
+    ok &= _pair_bwd_case(1, 256, 12544, 32)
+    return ok
+
+
+@case
+def pair_bwd_dense():
+    import torch
+    from heuristique_style_transfer_code_b200 import ops
+    from oracle import head_fp64 as O
+    ok = True
+    _opt("gram_bwd_pair", 1)
+    for (B, C, HW) in [(1, 64, 3136), (2, 256, 196), (1, 512, 100)]:
+        torch.manual_seed(0)
+        x = torch.relu(torch.randn(B, C, HW, device="cuda"))
+        dg = torch.randn(B, C, C, device="cuda")
+        df = ops.gram_dense_bwd(x, dg)
+        torch.cuda.synchronize()
+        e = O.rel_err(_np(df), O.gram_dense_backward(_np(x), _np(dg)))
+        print(f"pair-dense-bwd B={B} C={C} HW={HW}: rel_err vs fp64={e:.3e}", flush=True)
+        ok &= e < 3e-3
+    return ok
+
+
+def _time_us(fn, n=10, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(n):
+        fn()
+    ev[1].record()
+    torch.cuda.synchronize()
+    return ev[0].elapsed_time(ev[1]) / n * 1e3
+
+
+@case
+def timing_pair():
+    """Pair (TMA, cta_group::2) kernels against the ld.global-producer kernels, kernel-only, inputs larger than L2."""
+    import json
+    import torch
+    from heuristique_style_transfer_code_b200 import ops
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peaks = json.load(open(pk)) if os.path.exists(pk) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+    g = 32
+    for (B, C, HW) in [(256, 256, 3136), (256, 512, 784), (256, 1024, 196), (512, 256, 3136), (64, 512, 784), (1, 256, 12544)]:
+        for dt in ("f32", "bf16"):
+            x = torch.relu(torch.randn(B, C, HW, device="cuda"))
+            if dt == "bf16":
+                x = x.bfloat16()
+            es = x.element_size()
+            desc = torch.empty(B, 3, g * g, device="cuda")
+            dd = torch.randn(B, 3, g * g, device="cuda")
+            for pair in (1, 0):
+                _opt("gram_fwd_pair", pair)
+                us = _time_us(lambda: ops.gram_pool_fwd_(x, g, desc, 0))
+                by = B * C * HW * es + B * g * g * 4
+                fl = B * C * (C + 1) * HW
+                print(f"fwd {dt} B={B} C={C} HW={HW} pair={pair}: {us:8.1f} us  {by/us/1e3:8.1f} GB/s ({by/us/1e3/peaks['hbm_gbs']:.2f} of HBM)"
+                      f"  {fl/us/1e6:8.1f} TFLOP/s sym ({fl/us/1e6/peaks['bf16_tflops']:.2f} of bf16 tensor peak)", flush=True)
+            for pair in (1, 0):
+                _opt("gram_bwd_pair", pair)
+                us = _time_us(lambda: ops.gram_pool_bwd(x, g, dd, 0))
+                by = B * C * HW * (es + 4)
+                fl = 2 * B * C * C * HW
+                print(f"bwd {dt} B={B} C={C} HW={HW} pair={pair}: {us:8.1f} us  {by/us/1e3:8.1f} GB/s ({by/us/1e3/peaks['hbm_gbs']:.2f} of HBM)"
+                      f"  {fl/us/1e6:8.1f} TFLOP/s ({fl/us/1e6/peaks['bf16_tflops']:.2f} of bf16 tensor peak)", flush=True)
+            del x, desc, dd
+    _opt("gram_fwd_pair", -1)
+    _opt("gram_bwd_pair", -1)
+    return True
+
+
 def main():
     names = sys.argv[1:] or list(CASES)
     if len(names) == 1 and os.environ.get("GH_BRINGUP_CHILD") == "1":
@@ -395,7 +602,7 @@ def main():
         print(f"===== {name} =====", flush=True)
         env = dict(os.environ, GH_BRINGUP_CHILD="1")
         try:
-            rc = subprocess.run([sys.executable, os.path.abspath(__file__), name], env=env, timeout=420).returncode
+            rc = subprocess.run([sys.executable, os.path.abspath(__file__), name], env=env, timeout=int(os.environ.get("GH_CASE_TIMEOUT", "420"))).returncode
         except subprocess.TimeoutExpired:
             rc = "timeout"
         results[name] = rc
