@@ -9,6 +9,7 @@
 #include "gram_bwd_pair.cuh"
 #include "attn_head.cuh"
 #include "umma_gemm.cuh"
+#include "preprocess.cuh"
 #include <string>
 
 namespace gh {
@@ -540,6 +541,24 @@ int gh_attn_head_fwd(const float* desc, const float* W_in, const float* b_in, co
   if (e != cudaSuccess) return (int)e;
   // logits = emb W_c^T + b_c        (B, nc): nc is a handful of classes -> one warp per (image, class) dot product
   classifier_fwd_kernel<<<(B * nc + 3) / 4, 128, 0, st>>>(emb, W_c, b_c, logits, B, E, nc);
+  return (int)cudaGetLastError();
+}
+
+int gh_preprocess_frame(const unsigned char* frame, long long pitch_bytes, int H, int W, int bgr, const int* hx_min,
+                        const int* hx_size, const int* hk, int hkmax, const int* vy_min, const int* vy_size, const int* vk,
+                        int vkmax, const float* mean3_host, const float* std3_host, float* out, int OH, int OW,
+                        void* stream) {
+  if (!frame || !hx_min || !hx_size || !hk || !vy_min || !vy_size || !vk || !mean3_host || !std3_host || !out)
+    return GH_ERR_BAD_ARG;
+  if (H <= 0 || W <= 0 || OH <= 0 || OW <= 0 || hkmax <= 0 || vkmax <= 0 || pitch_bytes < 3LL * W) return GH_ERR_BAD_ARG;
+  if (OH > 65535) return GH_ERR_UNSUPPORTED;
+  PreprocParams p;
+  p.frame = frame; p.pitch = pitch_bytes; p.H = H; p.W = W; p.OH = OH; p.OW = OW;
+  p.hx_min = hx_min; p.hx_size = hx_size; p.hk = hk; p.hkmax = hkmax;
+  p.vy_min = vy_min; p.vy_size = vy_size; p.vk = vk; p.vkmax = vkmax;
+  p.out = out; p.bgr = bgr ? 1 : 0;
+  for (int c = 0; c < 3; ++c) { p.mean[c] = mean3_host[c]; p.std[c] = std3_host[c]; }
+  preprocess_frame_kernel<<<dim3((OW + 255) / 256, OH), 256, 0, (cudaStream_t)stream>>>(p);
   return (int)cudaGetLastError();
 }
 

@@ -1,0 +1,77 @@
+// Camera-mode preprocessing on the GPU: one kernel turns a raw BGR uint8 frame into the normalised fp32 CHW tensor the
+// encoder consumes, bit-identically to what the reference does on the host per frame
+// (functions/functions_RESNET50_Truncate_Gram_Attention.py:499-501: cv2.cvtColor(BGR2RGB) -> Image.fromarray ->
+// transform; test_RESNET50_Truncate_gram_attention.py:61-66: Resize [+ CenterCrop] + ToTensor + Normalize).
+//
+// torchvision's Resize on a PIL image is Pillow's ImagingResample with the bilinear (triangle) filter: separable,
+// support widened by the down-scale factor (antialiasing), 8-bit fixed point -- coefficients with 22 fractional bits,
+// a horizontal pass rounded to uint8, then a vertical pass rounded to uint8. The coefficient tables depend only on the
+// sizes; the host computes them once (streaming.py) and a CenterCrop is just the sub-range of output coordinates the
+// tables are built for. One thread = one output pixel (three channels): for every contributing input row it forms
+// the horizontally filtered uint8, then filters those vertically, divides by 255 and normalises in IEEE fp32.
+// The frame is read straight from the uploaded uint8 buffer (6 MB at 1080p, L2 resident); nothing else touches HBM.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gh {
+
+constexpr int kPreprocPrecisionBits = 32 - 8 - 2;
+
+struct PreprocParams {
+  const uint8_t* frame;     // (H, W, 3) uint8, `pitch` bytes between rows
+  long long pitch;
+  int H, W;
+  int OH, OW;               // output (after crop) extent
+  const int* hx_min;        // [OW]   first contributing input column
+  const int* hx_size;       // [OW]   number of contributing columns
+  const int* hk;            // [OW][hkmax] integer coefficients (sum = 2^22)
+  int hkmax;
+  const int* vy_min;        // [OH]
+  const int* vy_size;       // [OH]
+  const int* vk;            // [OH][vkmax]
+  int vkmax;
+  float* out;               // (3, OH, OW) fp32
+  int bgr;                  // 1: the frame is BGR and output channel c reads input channel 2 - c (cv2.cvtColor BGR2RGB)
+  float mean[3], std[3];
+};
+
+__device__ __forceinline__ int preproc_clip8(int acc) {
+  const int v = acc >> kPreprocPrecisionBits;
+  return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+
+__global__ void __launch_bounds__(256) preprocess_frame_kernel(const PreprocParams p) {
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  const int oy = blockIdx.y;
+  if (ox >= p.OW) return;
+  const int x0 = p.hx_min[ox], nx = p.hx_size[ox];
+  const int y0 = p.vy_min[oy], ny = p.vy_size[oy];
+  const int* __restrict__ hk = p.hk + (long long)ox * p.hkmax;
+  const int* __restrict__ vk = p.vk + (long long)oy * p.vkmax;
+  int acc[3] = {1 << (kPreprocPrecisionBits - 1), 1 << (kPreprocPrecisionBits - 1), 1 << (kPreprocPrecisionBits - 1)};
+  for (int j = 0; j < ny; ++j) {
+    const uint8_t* __restrict__ row = p.frame + (long long)(y0 + j) * p.pitch + (long long)x0 * 3;
+    int h0 = 1 << (kPreprocPrecisionBits - 1), h1 = h0, h2 = h0;
+    for (int i = 0; i < nx; ++i) {
+      const int k = __ldg(hk + i);
+      h0 += (int)__ldg(row + 3 * i) * k;
+      h1 += (int)__ldg(row + 3 * i + 1) * k;
+      h2 += (int)__ldg(row + 3 * i + 2) * k;
+    }
+    const int kv = __ldg(vk + j);
+    acc[0] += preproc_clip8(h0) * kv;
+    acc[1] += preproc_clip8(h1) * kv;
+    acc[2] += preproc_clip8(h2) * kv;
+  }
+  const long long plane = (long long)p.OH * p.OW;
+  float* o = p.out + (long long)oy * p.OW + ox;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int src = p.bgr ? 2 - c : c;
+    const float v = (float)preproc_clip8(acc[src]) / 255.0f;          // ToTensor
+    o[c * plane] = (v - p.mean[c]) / p.std[c];                        // Normalize (IEEE division: no fast-math)
+  }
+}
+
+}  // namespace gh

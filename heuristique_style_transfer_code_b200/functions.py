@@ -362,11 +362,16 @@ def plot_tsne_interactive(embeddings, labels, classes, img_paths, dataset, color
 # camera streaming  (:477-536)
 # ---------------------------------------------------------------------------------------------------------------------
 def run_camera(model, transform, class_names, save_video, save_dir, prob_threshold, measure_time, capture=None,
-               display=True, max_frames=None):
+               display=True, max_frames=None, pipeline="auto"):
     """Per frame: BGR->RGB -> PIL -> transform -> model -> softmax -> label overlay; optional video file and
     times_camera.json (:477-536). `capture`, `display`, `max_frames` are additions (defaults reproduce the reference:
     cv2.VideoCapture(0), cv2.imshow, run until 'q'): any object with read()/isOpened()/release() can stand in for the
-    camera, which is how the streaming benchmark feeds synthetic 1080p frames."""
+    camera, which is how the streaming benchmark feeds synthetic 1080p frames.
+
+    pipeline: "host" preprocesses every frame on the CPU exactly as the reference does; "gpu" uploads the raw frame and
+    runs streaming.CameraPipeline (bit-identical preprocessing kernel + CUDA-graph replay of the whole forward);
+    "auto" (default) takes the GPU pipeline when the model is on a CUDA device and `transform` is the
+    Resize [+ CenterCrop] + ToTensor + Normalize chain that kernel reproduces, the host path otherwise."""
     import cv2
     from PIL import Image
     model.eval()
@@ -381,17 +386,30 @@ def run_camera(model, transform, class_names, save_video, save_dir, prob_thresho
                               (640, 480))
     times = []
     frames = 0
+    gpu_pipe, tried_pipe = None, False
     with torch.no_grad():
         while max_frames is None or frames < max_frames:
             ok, frame = cap.read()
             if not ok:
                 print("Error: Unable to read the image from the camera")
                 break
+            if gpu_pipe is None and pipeline in ("auto", "gpu") and not tried_pipe:
+                tried_pipe = True
+                on_cuda = torch.device(model.device).type == "cuda"
+                if on_cuda:
+                    from .streaming import CameraPipeline
+                    gpu_pipe = CameraPipeline.from_transform(model, transform, frame.shape)
+                if gpu_pipe is None and pipeline == "gpu":
+                    raise ValueError("run_camera(pipeline='gpu') needs a CUDA model and a Resize [+ CenterCrop] + "
+                                     "ToTensor + Normalize transform")
             start = time.time()
-            rgb = cv2.cvtColor(frame, cv2.COLOR_BGR2RGB)
-            batch = transform(Image.fromarray(rgb)).unsqueeze(0).to(model.device)
-            _, outputs = model(batch)
-            probabilities = F.softmax(outputs, dim=1).cpu().numpy()[0]   # the .cpu() is the only sync, as upstream
+            if gpu_pipe is not None and frame.shape == gpu_pipe.frame_shape:
+                probabilities = gpu_pipe(frame)
+            else:
+                rgb = cv2.cvtColor(frame, cv2.COLOR_BGR2RGB)
+                batch = transform(Image.fromarray(rgb)).unsqueeze(0).to(model.device)
+                _, outputs = model(batch)
+                probabilities = F.softmax(outputs, dim=1).cpu().numpy()[0]   # the .cpu() is the only sync, as upstream
             best = int(np.argmax(probabilities))
             prob = probabilities[best]
             name = class_names[best] if prob >= prob_threshold else "Unknown"

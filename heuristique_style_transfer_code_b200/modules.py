@@ -14,10 +14,20 @@ on torch.autograd.set_detect_anomaly (the reference does so at import, :9).
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
 from . import ops
+
+# How the cuDNN backbone hands its stage activations to the head:
+#   "reference"          - exactly the reference's execution: fp32 NCHW, torch defaults (the default)
+#   "bf16"               - torch.autocast(bfloat16) around the encoder: bf16 NCHW activations
+#   "bf16_channels_last" - encoder converted to channels_last and run under bf16 autocast: bf16 NHWC activations
+# The two bf16 modes change the numerics of the BACKBONE (not of the head) and are therefore opt-in:
+# model.set_backbone_mode(...) or the environment variable GRAMHEAD_BACKBONE for unmodified reference scripts.
+BACKBONE_MODES = ("reference", "bf16", "bf16_channels_last")
 
 
 class GramAttentionHead:
@@ -39,6 +49,23 @@ class _TruncatedGramAttentionBase(nn.Module):
         self.gram_matrix_size = gram_matrix_size
         self.classifier = nn.Linear(self.gram_matrix_size ** 2, self.num_classes).to(self.device)
         self.attention = nn.MultiheadAttention(embed_dim=self.gram_matrix_size ** 2, num_heads=1).to(self.device)
+        self._backbone_mode = "reference"
+        env_mode = os.environ.get("GRAMHEAD_BACKBONE", "")
+        if env_mode:
+            self.set_backbone_mode(env_mode)
+
+    @property
+    def backbone_mode(self) -> str:
+        return self._backbone_mode
+
+    def set_backbone_mode(self, mode: str):
+        """Selects how the encoder runs (see BACKBONE_MODES). Parameters, state_dict keys and dtypes are unchanged."""
+        if mode not in BACKBONE_MODES:
+            raise ValueError(f"backbone mode must be one of {BACKBONE_MODES}, got {mode!r}")
+        fmt = torch.channels_last if mode == "bf16_channels_last" else torch.contiguous_format
+        self.truncated_encoder.to(memory_format=fmt)
+        self._backbone_mode = mode
+        return self
 
     def gram_matrix(self, activations):
         """(b, ch, h, w) -> (b, ch, ch): F F^T / (h*w), differentiable (dense tcgen05 Gram kernels)."""
@@ -46,6 +73,14 @@ class _TruncatedGramAttentionBase(nn.Module):
 
     def _stage_activations(self, x):
         x = x.to(self.device)
+        if self._backbone_mode == "reference":
+            return self._run_encoder(x)
+        if self._backbone_mode == "bf16_channels_last":
+            x = x.contiguous(memory_format=torch.channels_last)
+        with torch.autocast(device_type="cuda", dtype=torch.bfloat16):
+            return self._run_encoder(x)
+
+    def _run_encoder(self, x):
         enc = self.truncated_encoder
         # conv1, bn1, relu, maxpool -- an encoder truncated below 4 children raises IndexError, as the reference does
         x = enc[0](x)

@@ -94,6 +94,20 @@ int gh_attn_head_fwd(const float* desc, const float* W_in, const float* b_in, co
                      const float* W_c, const float* b_c, int B, int L, int E, int nc, float* qkv, float* probs,
                      float* obar, float* emb, float* logits, void* stream);
 
+/* Camera-mode preprocessing of one frame on the GPU, bit-identical to the reference's per-frame host code
+ *   functions/functions_RESNET50_Truncate_Gram_Attention.py:499-501  cv2.cvtColor(BGR2RGB) -> Image.fromarray -> transform
+ *   test_RESNET50_Truncate_gram_attention.py:61-66                   Resize [+ CenterCrop] + ToTensor + Normalize
+ * (torchvision Resize on a PIL image = Pillow's fixed-point, antialiased bilinear ImagingResample).
+ * frame: (H, W, 3) uint8 on the device, pitch_bytes between rows; bgr != 0: channels are B,G,R (OpenCV).
+ * hx_min/hx_size [OW], hk [OW][hkmax]: per output column the first contributing input column, their number and
+ * the 22-bit fixed-point coefficients; vy_min/vy_size [OH], vk [OH][vkmax]: the same for rows. A centre crop is the
+ * sub-range of output coordinates the tables are built for (streaming.py computes them once per geometry).
+ * mean3_host / std3_host: HOST pointers to 3 floats. out: (3, OH, OW) fp32 = (x/255 - mean) / std. */
+int gh_preprocess_frame(const unsigned char* frame, long long pitch_bytes, int H, int W, int bgr, const int* hx_min,
+                        const int* hx_size, const int* hk, int hkmax, const int* vy_min, const int* vy_size, const int* vk,
+                        int vkmax, const float* mean3_host, const float* std3_host, float* out, int OH, int OW,
+                        void* stream);
+
 /* The GEMM the attention entry points are built from, exposed for testing and reuse:
  *   D[m*ldd + n] = sum_k A[m*a_sm + k*a_sk] * B[k*b_sk + n*b_sn] (+ bias[n]),   fp32 in, fp32 out.
  * Runs on tcgen05 with split-bf16 operands (hi*hi + hi*lo + lo*hi, fp32 accumulate: ~1e-5 relative) when each operand
