@@ -248,18 +248,22 @@ def run_ours(args):
         head_ms = timed_region(head_only, args.steps, device, D) / args.steps
     del stages
 
-    # ---- end to end through the public call: host batch in, logits + embeddings out ----
-    def e2e_step():
-        with torch.no_grad():
-            emb, logits = model(x_host)                 # forward() moves the pinned batch to self.device (H2D)
-            if world > 1:
-                logits = D.gather_rows(logits, total, world)
-                emb = D.gather_rows(emb, total, world)
-            return emb.cpu(), logits.cpu()              # D2H of the results (the synchronisation point, as upstream)
+    # ---- end to end through the public API: pinned host batches in, logits + embeddings back on the host ----
+    # The loop is the package's evaluation loop shape (functions.evaluate_model_test): cuda_prefetch uploads batch i+1
+    # on a side stream while batch i is in the model; every step's H2D copy and D2H read are inside the timed region.
+    from heuristique_style_transfer_code_b200.functions import cuda_prefetch
 
-    for _ in range(2):
-        e2e_step()
-    e2e_ms = timed_region(e2e_step, args.steps, device, D)
+    def e2e_loop(n):
+        with torch.no_grad():
+            for (xb,) in cuda_prefetch(((x_host,) for _ in range(n)), device):
+                emb, logits = model(xb)
+                if world > 1:
+                    logits = D.gather_rows(logits, total, world)
+                    emb = D.gather_rows(emb, total, world)
+                emb.cpu(), logits.cpu()                 # D2H of the results (the synchronisation point, as upstream)
+
+    e2e_loop(2)
+    e2e_ms = timed_region(lambda: e2e_loop(args.steps), 1, device, D)
     e2e_value = total * args.steps / (e2e_ms / 1e3)
     h2d = B * 3 * IMAGE * IMAGE * 4
     d2h = total * (GRAM_SIZE * GRAM_SIZE + NUM_CLASSES) * 4

@@ -193,3 +193,14 @@ def test_loops_run_with_a_cpu_stand_in_model(tmp_path):
     tester = PortModel(base, 5, 3, 8, return_embeddings=True)
     emb, preds, labels, probs, paths = F.evaluate_model_test(tester, loader, "cpu")
     assert emb.shape == (6, 64) and probs.shape == (6, 3) and len(paths) == 6 and paths[4] == "img_4.png"
+
+
+def test_cuda_prefetch_passes_batches_through_in_order_on_cpu():
+    import torch
+    from heuristique_style_transfer_code_b200.functions import cuda_prefetch
+    batches = [(torch.full((2, 3), float(i)), torch.tensor([i, i])) for i in range(5)]
+    out = list(cuda_prefetch(iter(batches), "cpu"))
+    assert len(out) == 5
+    for i, (x, y) in enumerate(out):
+        assert torch.equal(x, batches[i][0]) and torch.equal(y, batches[i][1])
+    assert list(cuda_prefetch(iter([]), "cpu")) == []

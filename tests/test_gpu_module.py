@@ -111,3 +111,18 @@ def test_checkpoint_roundtrip_through_functions(pair, tmp_path):
         a, b = ours(x), other(x)
     # same weights -> same outputs up to fp32 summation order (split-K atomics, cuDNN algorithm choice)
     assert torch.allclose(a[1], b[1], rtol=1e-3, atol=1e-4)
+
+
+def test_cuda_prefetch_overlapped_upload_keeps_order_and_values():
+    import torch
+    from heuristique_style_transfer_code_b200.functions import cuda_prefetch
+    host = [(torch.randn(64, 3, 32, 32).pin_memory(), torch.full((64,), i)) for i in range(6)]
+    seen = []
+    for x, y in cuda_prefetch(iter(host), "cuda:0"):
+        assert x.is_cuda and y.is_cuda
+        seen.append((x.clone(), y.clone()))
+        torch.cuda._sleep(200000)           # keep the main stream busy while the next upload runs
+    torch.cuda.synchronize()
+    assert len(seen) == 6
+    for (x, y), (hx, hy) in zip(seen, host):
+        assert torch.equal(x.cpu(), hx) and torch.equal(y.cpu(), hy)
