@@ -75,6 +75,52 @@ def _feature_view(x: torch.Tensor) -> Tuple[torch.Tensor, int, int, int, int, in
     return x, code, x.stride(0), x.stride(1), b, c, hw
 
 
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return GH_DTYPE_F32
+    if t.dtype == torch.bfloat16:
+        return GH_DTYPE_BF16
+    raise GramHeadError(f"gramhead: features must be float32 or bfloat16, got {t.dtype}")
+
+
+def is_channels_last(x: torch.Tensor) -> bool:
+    """Dense NHWC storage of a (B, C, H, W) tensor with more than one channel and more than one position."""
+    if x.dim() != 4:
+        return False
+    b, c, h, w = x.shape
+    return (c > 1 and h * w > 1 and x.stride(1) == 1 and x.stride(3) == c and x.stride(2) == w * c
+            and x.stride(0) == h * w * c)
+
+
+def nhwc_to_nchw(x: torch.Tensor) -> torch.Tensor:
+    """NCHW-contiguous copy of a channels_last activation (same dtype): the C x HW matrices gram_matrix() views
+    (reference Models/...:27-28), produced by the library's transpose kernel in one HBM-bound pass."""
+    _require_cuda(x, "features")
+    b, c, h, w = x.shape
+    out = torch.empty((b, c, h, w), dtype=x.dtype, device=x.device)
+    code = _dtype_code(x)
+    work = dict(bytes=2 * x.numel() * x.element_size(), flops=0, kind="transpose")
+    with torch.cuda.device(x.device), _Timed(f"nhwc_to_nchw[C={c},HW={h * w},{x.dtype}]", 1, x.device, **work):
+        rc = _lib.lib().gh_transpose_cast(x.data_ptr(), code, out.data_ptr(), code, b, h * w, c, _stream_ptr(x))
+    check(rc, "gh_transpose_cast")
+    return out
+
+
+def grad_like_activation(df: torch.Tensor, shape, dtype, channels_last: bool) -> torch.Tensor:
+    """fp32 (B, C, HW) gradient -> gradient tensor of the activation's shape and dtype; for a channels_last activation
+    the transpose kernel writes it NHWC (and casts) directly, so the cuDNN backward gets the layout it runs in."""
+    if not channels_last:
+        return df.view(shape).to(dtype)
+    b, c, h, w = shape
+    out = torch.empty((b, c, h, w), dtype=dtype, device=df.device, memory_format=torch.channels_last)
+    work = dict(bytes=df.numel() * (4 + out.element_size()), flops=0, kind="transpose")
+    with torch.cuda.device(df.device), _Timed(f"nchw_to_nhwc[C={c},HW={h * w},{dtype}]", 1, df.device, **work):
+        rc = _lib.lib().gh_transpose_cast(df.data_ptr(), GH_DTYPE_F32, out.data_ptr(), _dtype_code(out), b, c, h * w,
+                                          _stream_ptr(df))
+    check(rc, "gh_transpose_cast")
+    return out
+
+
 def pooled_supported(c: int, g: int) -> bool:
     """True when the fused Gram+pool kernels apply (bins are disjoint k x k blocks, k a power of two in [8, 128])."""
     if g <= 0 or c % g:
@@ -174,6 +220,9 @@ class _GramDense(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x):
+        ctx.meta = (tuple(x.shape), x.dtype, is_channels_last(x))
+        if ctx.meta[2]:
+            x = nhwc_to_nchw(x)
         ctx.save_for_backward(x)
         return gram_dense_fwd(x)
 
@@ -181,7 +230,7 @@ class _GramDense(torch.autograd.Function):
     def backward(ctx, d_gram):
         (x,) = ctx.saved_tensors
         df = gram_dense_bwd(x, d_gram)
-        return df.view(x.shape).to(x.dtype)
+        return grad_like_activation(df, *ctx.meta)
 
 
 def gram_matrix(x: torch.Tensor) -> torch.Tensor:
@@ -196,6 +245,10 @@ class _StyleDescriptor(torch.autograd.Function):
         b = stages[0].shape[0]
         L = len(stages)
         desc = torch.empty((b, L, g * g), device=stages[0].device, dtype=torch.float32)
+        ctx.meta = [(tuple(x.shape), x.dtype, is_channels_last(x)) for x in stages]
+        # channels_last (NHWC) activations: one transpose pass gives the C x HW matrices the Gram kernels consume; the
+        # NCHW copy is what backward re-reads, so it is the tensor saved (the backbone keeps the original alive anyway)
+        stages = [nhwc_to_nchw(x) if m[2] else x for x, m in zip(stages, ctx.meta)]
         for l, x in enumerate(stages):
             if pooled_supported(x.shape[1], g):
                 gram_pool_fwd_(x, g, desc, l)
@@ -219,7 +272,7 @@ class _StyleDescriptor(torch.autograd.Function):
                 df = gram_pool_bwd(x, g, d_desc, l)
             else:
                 df = gram_dense_bwd(x, adaptive_pool_bwd(d_desc, l, c, g))
-            grads.append(df.view(x.shape).to(x.dtype))
+            grads.append(grad_like_activation(df, *ctx.meta[l]))
         return tuple(grads)
 
 

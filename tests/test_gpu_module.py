@@ -126,3 +126,74 @@ def test_cuda_prefetch_overlapped_upload_keeps_order_and_values():
     assert len(seen) == 6
     for (x, y), (hx, hy) in zip(seen, host):
         assert torch.equal(x.cpu(), hx) and torch.equal(y.cpu(), hy)
+
+
+@pytest.mark.parametrize("B,R,S", [(3, 196, 1024), (2, 3136, 256), (2, 50, 70), (1, 1, 5), (2, 65, 129)])
+def test_transpose_cast_kernel_is_exact(B, R, S):
+    import torch
+    from heuristique_style_transfer_code_b200 import _lib
+    lib = _lib.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    torch.manual_seed(0)
+    for tin, cin in ((torch.float32, 0), (torch.bfloat16, 1)):
+        for tout, cout in ((torch.float32, 0), (torch.bfloat16, 1)):
+            x = torch.randn(B, R, S, device="cuda").to(tin)
+            out = torch.empty(B, S, R, device="cuda", dtype=tout)
+            assert lib.gh_transpose_cast(x.data_ptr(), cin, out.data_ptr(), cout, B, R, S, st) == 0
+            torch.cuda.synchronize()
+            assert torch.equal(out, x.transpose(1, 2).to(tout))     # same round-to-nearest-even cast as torch
+
+
+def test_channels_last_activations_take_the_transpose_path_and_match_nchw():
+    import torch
+    from heuristique_style_transfer_code_b200 import ops
+    torch.manual_seed(0)
+    g = 32
+    for dtype in (torch.bfloat16, torch.float32):
+        shapes = [(4, 256, 56, 56), (4, 512, 28, 28), (4, 1024, 14, 14)]
+        base = [torch.relu(torch.randn(s, device="cuda")).to(dtype) for s in shapes]
+        a = [t.clone().requires_grad_(True) for t in base]
+        b = [t.clone().contiguous(memory_format=torch.channels_last).requires_grad_(True) for t in base]
+        assert all(ops.is_channels_last(t) for t in b) and not any(ops.is_channels_last(t) for t in a)
+        ops.KSPLIT = 1
+        try:
+            da, db = ops.style_descriptor(a, g), ops.style_descriptor(b, g)
+            w = torch.randn_like(da)
+            (da * w).sum().backward()
+            (db * w).sum().backward()
+            Ga, Gb = ops.gram_matrix(a[1].detach()), ops.gram_matrix(b[1].detach())
+        finally:
+            ops.KSPLIT = 0
+        torch.cuda.synchronize()
+        assert torch.equal(da, db)                                   # same C x HW matrices reach the same kernels
+        for ta, tb in zip(a, b):
+            assert ops.is_channels_last(tb.grad) and tb.grad.dtype == dtype
+            assert torch.equal(ta.grad, tb.grad.contiguous())
+        assert torch.equal(Ga, Gb)
+
+
+def test_backbone_modes_agree_with_the_reference_mode():
+    import torch
+    from torchvision import models
+    from heuristique_style_transfer_code_b200 import TruncatedResNet50
+    torch.manual_seed(0)
+    model = TruncatedResNet50(models.resnet50(weights=None), 7, 4, 32, device="cuda").train()
+    x = torch.randn(8, 3, 224, 224, device="cuda")
+    y = torch.randint(0, 4, (8,), device="cuda")
+    outs, grads = {}, {}
+    for mode in ("reference", "bf16", "bf16_channels_last"):
+        model.set_backbone_mode(mode)
+        assert model.backbone_mode == mode
+        model.zero_grad(set_to_none=True)
+        logits = model(x)
+        torch.nn.functional.cross_entropy(logits, y).backward()
+        outs[mode] = logits.detach().float()
+        grads[mode] = model.attention.in_proj_weight.grad.detach().clone()
+        assert all(p.dtype == torch.float32 for p in model.parameters())        # parameters stay fp32
+    model.set_backbone_mode("reference")
+    for mode in ("bf16", "bf16_channels_last"):
+        rel = float((outs[mode] - outs["reference"]).norm() / outs["reference"].norm())
+        grel = float((grads[mode] - grads["reference"]).norm() / grads["reference"].norm())
+        assert rel <= 3e-2 and grel <= 1e-1, (mode, rel, grel)      # bf16 backbone: ~1e-2 on activations
+    with pytest.raises(ValueError):
+        model.set_backbone_mode("fp8")
