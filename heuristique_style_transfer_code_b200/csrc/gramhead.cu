@@ -545,21 +545,22 @@ int gh_attn_head_fwd(const float* desc, const float* W_in, const float* b_in, co
   return (int)cudaGetLastError();
 }
 
-int gh_transpose_cast(const void* in, int in_dtype, void* out, int out_dtype, int B, int R, int S, void* stream) {
-  if (!in || !out || B <= 0 || R <= 0 || S <= 0) return GH_ERR_BAD_ARG;
+int gh_transpose_cast(const void* in, int in_dtype, void* out, int out_dtype, int B, int R, int S, long long out_pitch,
+                      void* stream) {
+  if (!in || !out || B <= 0 || R <= 0 || S <= 0 || out_pitch < R) return GH_ERR_BAD_ARG;
   if ((in_dtype != GH_DTYPE_F32 && in_dtype != GH_DTYPE_BF16) || (out_dtype != GH_DTYPE_F32 && out_dtype != GH_DTYPE_BF16))
     return GH_ERR_BAD_ARG;
   if (B > 65535 || (R + 63) / 64 > 65535) return GH_ERR_UNSUPPORTED;
   const dim3 grid((S + 63) / 64, (R + 63) / 64, B), block(64, 4);
   cudaStream_t st = (cudaStream_t)stream;
   if (in_dtype == GH_DTYPE_F32 && out_dtype == GH_DTYPE_F32)
-    transpose_cast_kernel<float, float><<<grid, block, 0, st>>>((const float*)in, (float*)out, R, S);
+    transpose_cast_kernel<float, float><<<grid, block, 0, st>>>((const float*)in, (float*)out, R, S, out_pitch);
   else if (in_dtype == GH_DTYPE_F32)
-    transpose_cast_kernel<float, __nv_bfloat16><<<grid, block, 0, st>>>((const float*)in, (__nv_bfloat16*)out, R, S);
+    transpose_cast_kernel<float, __nv_bfloat16><<<grid, block, 0, st>>>((const float*)in, (__nv_bfloat16*)out, R, S, out_pitch);
   else if (out_dtype == GH_DTYPE_BF16)
-    transpose_cast_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, R, S);
+    transpose_cast_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, R, S, out_pitch);
   else
-    transpose_cast_kernel<__nv_bfloat16, float><<<grid, block, 0, st>>>((const __nv_bfloat16*)in, (float*)out, R, S);
+    transpose_cast_kernel<__nv_bfloat16, float><<<grid, block, 0, st>>>((const __nv_bfloat16*)in, (float*)out, R, S, out_pitch);
   return (int)cudaGetLastError();
 }
 

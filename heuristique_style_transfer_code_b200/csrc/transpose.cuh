@@ -1,4 +1,5 @@
-// Batched 2-D transpose with optional fp32 -> bf16 cast:  out[b][s][r] = cast(in[b][r][s]).
+// Batched 2-D transpose with optional fp32 -> bf16 cast:  out[b][s][r] = cast(in[b][r][s]), output rows `out_pitch`
+// elements apart (>= R: lets the caller pad C x HW rows to the 16 B multiple a TMA tensor map needs, e.g. HW = 196 bf16).
 //
 // Hand-off between a channels_last (NHWC) backbone and the Gram kernels: the reference's
 // gram_matrix() starts with activations.view(b, ch, h*w) (Models/Models_RESNET50_TRUNCATE_GRAM_with_Attention.py:27-28),
@@ -31,9 +32,11 @@ __device__ __forceinline__ void tr_store<__nv_bfloat16>(__nv_bfloat16* p, float 
 
 // grid (ceil(S/64), ceil(R/64), B), block (64, 4)
 template <typename TI, typename TO>
-__global__ void __launch_bounds__(256) transpose_cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, int R, int S) {
+__global__ void __launch_bounds__(256) transpose_cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, int R, int S,
+                                                             long long out_pitch) {
   __shared__ float tile[64][65];
   const long long img = (long long)blockIdx.z * R * S;
+  const long long img_out = (long long)blockIdx.z * S * out_pitch;
   const int s0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
   const int tx = threadIdx.x, ty = threadIdx.y;
 #pragma unroll
@@ -45,7 +48,7 @@ __global__ void __launch_bounds__(256) transpose_cast_kernel(const TI* __restric
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const int s = s0 + ty + 4 * i, r = r0 + tx;
-    if (r < R && s < S) tr_store<TO>(out + img + (long long)s * R + r, tile[tx][ty + 4 * i]);
+    if (r < R && s < S) tr_store<TO>(out + img_out + (long long)s * out_pitch + r, tile[tx][ty + 4 * i]);
   }
 }
 

@@ -93,17 +93,21 @@ def is_channels_last(x: torch.Tensor) -> bool:
 
 
 def nhwc_to_nchw(x: torch.Tensor) -> torch.Tensor:
-    """NCHW-contiguous copy of a channels_last activation (same dtype): the C x HW matrices gram_matrix() views
-    (reference Models/...:27-28), produced by the library's transpose kernel in one HBM-bound pass."""
+    """(B, C, HW)-shaped copy of a channels_last activation (same dtype): the C x HW matrices gram_matrix() views
+    (reference Models/...:27-28), produced by the library's transpose kernel in one HBM-bound pass. Rows are padded to
+    a multiple of 16 B (HW = 196 in bf16 -> pitch 200) so that every stage qualifies for the TMA-fed kernels."""
     _require_cuda(x, "features")
     b, c, h, w = x.shape
-    out = torch.empty((b, c, h, w), dtype=x.dtype, device=x.device)
+    hw = h * w
+    per16 = 16 // x.element_size()                       # rows padded to 16 B: what a TMA tensor map can describe
+    pitch = (hw + per16 - 1) // per16 * per16
+    buf = torch.empty((b, c, pitch), dtype=x.dtype, device=x.device)
     code = _dtype_code(x)
     work = dict(bytes=2 * x.numel() * x.element_size(), flops=0, kind="transpose")
-    with torch.cuda.device(x.device), _Timed(f"nhwc_to_nchw[C={c},HW={h * w},{x.dtype}]", 1, x.device, **work):
-        rc = _lib.lib().gh_transpose_cast(x.data_ptr(), code, out.data_ptr(), code, b, h * w, c, _stream_ptr(x))
+    with torch.cuda.device(x.device), _Timed(f"nhwc_to_nchw[C={c},HW={hw},{x.dtype}]", 1, x.device, **work):
+        rc = _lib.lib().gh_transpose_cast(x.data_ptr(), code, buf.data_ptr(), code, b, hw, c, pitch, _stream_ptr(x))
     check(rc, "gh_transpose_cast")
-    return out
+    return buf[:, :, :hw] if pitch != hw else buf.view(b, c, h, w)
 
 
 def grad_like_activation(df: torch.Tensor, shape, dtype, channels_last: bool) -> torch.Tensor:
@@ -115,7 +119,7 @@ def grad_like_activation(df: torch.Tensor, shape, dtype, channels_last: bool) ->
     out = torch.empty((b, c, h, w), dtype=dtype, device=df.device, memory_format=torch.channels_last)
     work = dict(bytes=df.numel() * (4 + out.element_size()), flops=0, kind="transpose")
     with torch.cuda.device(df.device), _Timed(f"nchw_to_nhwc[C={c},HW={h * w},{dtype}]", 1, df.device, **work):
-        rc = _lib.lib().gh_transpose_cast(df.data_ptr(), GH_DTYPE_F32, out.data_ptr(), _dtype_code(out), b, c, h * w,
+        rc = _lib.lib().gh_transpose_cast(df.data_ptr(), GH_DTYPE_F32, out.data_ptr(), _dtype_code(out), b, c, h * w, c,
                                           _stream_ptr(df))
     check(rc, "gh_transpose_cast")
     return out

@@ -94,13 +94,15 @@ int gh_attn_head_fwd(const float* desc, const float* W_in, const float* b_in, co
                      const float* W_c, const float* b_c, int B, int L, int E, int nc, float* qkv, float* probs,
                      float* obar, float* emb, float* logits, void* stream);
 
-/* Batched transpose with optional cast: out[b][s][r] = cast(in[b][r][s]); in (B, R, S), out (B, S, R), both dense;
- * dtypes GH_DTYPE_F32 / GH_DTYPE_BF16 in any combination. Hand-off with a channels_last (NHWC) backbone: the
+/* Batched transpose with optional cast: out[b][s][r] = cast(in[b][r][s]); in (B, R, S) dense, out (B, S, out_pitch)
+ * with out_pitch >= R elements between rows (padding a C x HW matrix's rows to a multiple of 16 B makes it
+ * describable by a TMA tensor map, e.g. HW = 196 in bf16); dtypes GH_DTYPE_F32 / GH_DTYPE_BF16 in any combination. Hand-off with a channels_last (NHWC) backbone: the
  * reference's gram_matrix() begins with activations.view(b, ch, h*w)
  * (Models/Models_RESNET50_TRUNCATE_GRAM_with_Attention.py:27-28) and so needs each image as a C x HW matrix with HW
  * contiguous; an NHWC activation is the HW x C transpose of it (forward: R = HW, S = C), and the fp32 NCHW gradient
  * goes back to NHWC in the activation's dtype (backward: R = C, S = HW). */
-int gh_transpose_cast(const void* in, int in_dtype, void* out, int out_dtype, int B, int R, int S, void* stream);
+int gh_transpose_cast(const void* in, int in_dtype, void* out, int out_dtype, int B, int R, int S, long long out_pitch,
+                      void* stream);
 
 /* Camera-mode preprocessing of one frame on the GPU, bit-identical to the reference's per-frame host code
  *   functions/functions_RESNET50_Truncate_Gram_Attention.py:499-501  cv2.cvtColor(BGR2RGB) -> Image.fromarray -> transform

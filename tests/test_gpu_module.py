@@ -138,10 +138,12 @@ def test_transpose_cast_kernel_is_exact(B, R, S):
     for tin, cin in ((torch.float32, 0), (torch.bfloat16, 1)):
         for tout, cout in ((torch.float32, 0), (torch.bfloat16, 1)):
             x = torch.randn(B, R, S, device="cuda").to(tin)
-            out = torch.empty(B, S, R, device="cuda", dtype=tout)
-            assert lib.gh_transpose_cast(x.data_ptr(), cin, out.data_ptr(), cout, B, R, S, st) == 0
+            pitch = R + 3
+            out = torch.full((B, S, pitch), -7.0, device="cuda", dtype=tout)
+            assert lib.gh_transpose_cast(x.data_ptr(), cin, out.data_ptr(), cout, B, R, S, pitch, st) == 0
             torch.cuda.synchronize()
-            assert torch.equal(out, x.transpose(1, 2).to(tout))     # same round-to-nearest-even cast as torch
+            assert torch.equal(out[:, :, :R], x.transpose(1, 2).to(tout))   # same round-to-nearest-even cast as torch
+            assert bool((out[:, :, R:] == -7.0).all())                      # the padding is not written
 
 
 def test_channels_last_activations_take_the_transpose_path_and_match_nchw():
