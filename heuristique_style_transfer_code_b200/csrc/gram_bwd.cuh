@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(kGbThreads, 1) gram_bwd_kernel(const GramBwdPa
       for (int kb = 0; kb < p.nkb; ++kb) {
         mbar_wait(bar_full + 8 * stage, phase, 300u + stage);
         tc_fence_after_sync();
-        if (lane == 0) {
+        if (elect_one()) {   // elect.sync, not a lane test: see gram_fwd_pair.cuh
           const uint32_t a_smem = smem_base + stage * p.stage_bytes;
           const uint32_t b_smem = a_smem + kGbATileBytes;
 #pragma unroll

@@ -222,7 +222,7 @@ __device__ __forceinline__ void gb2_issue_unit(const GramBwd2Params& p, uint32_t
   for (int kb = 0; kb < p.nkb; ++kb) {
     mbar_wait(bar_full + 8 * stage, phase, 300u + stage);
     tc_fence_after_sync();
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync, not a lane test: see gram_fwd_pair.cuh
       const uint32_t a_smem = smem_base + stage * stage_bytes;
       const uint32_t b_smem = a_smem + 2 * kB2ATileBytes;
 #pragma unroll

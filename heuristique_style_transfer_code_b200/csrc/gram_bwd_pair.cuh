@@ -14,9 +14,12 @@
 //   D = dF  [128 c][NT x]  per CTA in TMEM, two accumulator buffers: the epilogue of unit i overlaps the MMAs of i+1
 //   epilogue: tcgen05.ld (lane = channel, 32 positions) -> *scale -> swizzled staging tile -> TMA store, so the
 //             4 B/element gradient leaves the SM as full 128 B lines without occupying the LSU
-// Warps: 0 = TMA producer, 1 = TMEM owner + MMA issuer (leader CTA only), 2-5 = epilogue, 6-21 = A-tile generators
-// in four groups of four warps; group i owns ring stage i, so four K chunks are generated concurrently and the
-// per-chunk handshake (mbarrier wait, proxy fence, arrive) of one group overlaps the stores of the others.
+// Warps: 0 and 22 = TMA producers (even / odd K chunks), 1 = TMEM owner + MMA issuer (leader CTA only), 2-5 = epilogue,
+// 6-21 = A-tile generators in four groups of four warps; group i owns A-ring stage i, so four K chunks are generated
+// concurrently and the per-chunk handshake (mbarrier wait, proxy fence, arrive) of one group overlaps the stores of
+// the others. A and B tiles travel in separate rings: 5 stages of generated A, 5 stages (80 KB) of TMA-loaded F, 3 store
+// staging tiles per epilogue warp -- the best of the depth sweep in profiles/ (6 B stages are faster for C >= 512 but
+// 20 % slower on the HBM-bound C = 256 stage).
 #pragma once
 #include "pair.cuh"
 #include "gram_fwd.cuh"   // GramMode
@@ -24,18 +27,33 @@
 
 namespace gh {
 
-constexpr int kBpStages = 4;
+// Two rings. The generated A tiles have a short refill round trip (commit -> empty -> 8 stores -> proxy fence -> remote
+// arrive, well under a microsecond), the F tiles come from HBM / L2 with 1-2 us of loaded latency: bytes in flight =
+// bandwidth x latency, so the B ring is as deep as shared memory allows and the A ring only as deep as it must be.
+#ifndef GH_BP_A_STAGES
+#define GH_BP_A_STAGES 5
+#endif
+#ifndef GH_BP_B_STAGES
+#define GH_BP_B_STAGES 5
+#endif
+#ifndef GH_BP_STORE_BUFS
+#define GH_BP_STORE_BUFS 3
+#endif
+constexpr int kBpAStages = GH_BP_A_STAGES;                  // A ring; generator group i fills A stages i, i + 4, ...
+constexpr int kBpBStages = GH_BP_B_STAGES;                  // B ring (TMA loads of F)
 constexpr uint32_t kBpTileBytes = 16384;                    // A: [128 c][128 B]; B: <= 128 x-columns x (K chunk) x elem
-constexpr uint32_t kBpStageBytes = 2 * kBpTileBytes;
-constexpr int kBpStoreBufs = 4;                             // staging tiles per epilogue warp = TMA stores it keeps in flight
+constexpr int kBpStoreBufs = GH_BP_STORE_BUFS;              // staging tiles per epilogue warp = TMA stores it keeps in flight
 constexpr uint32_t kBpStoreBytes = 4 * kBpStoreBufs * 4096; // per epilogue warp: kBpStoreBufs [32 c][32 x] fp32 staging tiles
 constexpr int kBpMaxG = 32;                                 // pooled size handled here (larger g: the ldg kernels)
-constexpr int kBpGroups = kBpStages;                        // generator groups; group i fills ring stage i
+constexpr int kBpGroups = 4;                                // generator groups (four warps each); group i generates chunks n = i mod 4
 constexpr int kBpTableFloats = kBpMaxG * kBpMaxG + kBpMaxG; // g x g table + one row of zeros (rows beyond C)
-constexpr uint32_t kBpSymBytes = kBpGroups * 2 * kBpTableFloats * 4;   // per group: current and next image's table
-constexpr uint32_t kBpSmemBytes = kBpStages * kBpStageBytes + kBpStoreBytes + kBpSymBytes + 1024 + 256;
+constexpr uint32_t kBpSymBytes = 2 * kBpTableFloats * 4;    // current and next image's table, shared by the groups
+constexpr uint32_t kBpSmemBytes = (kBpAStages + kBpBStages) * kBpTileBytes + kBpStoreBytes + kBpSymBytes + 1024 + 256;
 constexpr int kBpGroupThreads = 128;                        // one thread per A row
-constexpr int kBpThreads = 6 * 32 + kBpGroups * kBpGroupThreads;
+constexpr int kBpGenThreads = kBpGroups * kBpGroupThreads;
+constexpr int kBpProducer2Warp = 6 + kBpGenThreads / 32;    // second TMA producer warp (the last one)
+constexpr int kBpThreads = (kBpProducer2Warp + 1) * 32;
+static_assert(kBpSmemBytes <= 232448, "gram_bwd_pair: shared memory budget");
 
 struct GramBwdPairParams {
   int B, C, HW;
@@ -81,12 +99,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t store_smem = smem_base + kBpStages * kBpStageBytes;
+  const uint32_t a_ring = smem_base;                                        // kBpAStages x 16 KB
+  const uint32_t b_ring = a_ring + kBpAStages * kBpTileBytes;               // kBpBStages x 16 KB
+  const uint32_t store_smem = b_ring + kBpBStages * kBpTileBytes;
   const uint32_t sym_smem = store_smem + kBpStoreBytes;
   float* sym = reinterpret_cast<float*>(smem_raw + (sym_smem - smem_u32(smem_raw)));
   const uint32_t bars = sym_smem + kBpSymBytes;
-  const uint32_t bar_full = bars, bar_empty = bars + 8 * kBpStages;
-  const uint32_t bar_tfull = bars + 16 * kBpStages, bar_tempty = bar_tfull + 16;
+  const uint32_t bar_fullA = bars, bar_emptyA = bar_fullA + 8 * kBpAStages;
+  const uint32_t bar_fullB = bar_emptyA + 8 * kBpAStages, bar_emptyB = bar_fullB + 8 * kBpBStages;
+  const uint32_t bar_tfull = bar_emptyB + 8 * kBpBStages, bar_tempty = bar_tfull + 16;
   const uint32_t tmem_slot = bar_tempty + 16;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -97,9 +118,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmF);
     tma_prefetch_desc(&tmD);
-    for (int s = 0; s < kBpStages; ++s) {
-      mbar_init(bar_full + 8 * s, 1 + 2 * (kBpGroupThreads / 32)); // leader's expect_tx + the stage's generator warps of both CTAs
-      mbar_init(bar_empty + 8 * s, 1);
+    for (int s = 0; s < kBpAStages; ++s) {
+      mbar_init(bar_fullA + 8 * s, 2 * (kBpGroupThreads / 32));   // the stage's generator warps of both CTAs
+      mbar_init(bar_emptyA + 8 * s, 1);                           // multicast tcgen05.commit
+    }
+    for (int s = 0; s < kBpBStages; ++s) {
+      mbar_init(bar_fullB + 8 * s, 1);                            // leader's expect_tx; both CTAs' TMA bytes land on it
+      mbar_init(bar_emptyB + 8 * s, 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
@@ -113,59 +138,82 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const uint32_t full_leader = mapa_u32(bar_full, 0);      // shared::cluster addresses of the leader's barriers
+  const uint32_t fullA_leader = mapa_u32(bar_fullA, 0);    // shared::cluster addresses of the leader's barriers
+  const uint32_t fullB_leader = mapa_u32(bar_fullB, 0);
   const uint32_t tempty_leader = mapa_u32(bar_tempty, 0);
   const int na = (p.NT / 2 + (int)KC - 1) / (int)KC;       // 128 B-wide x blocks each CTA loads per K chunk
+  // One thread per warp issues the TMA / tcgen05 instructions; elect.sync (not `lane == 0`) lets ptxas feed their
+  // uniform-register operands directly instead of wrapping each one in an elect-broadcast-retry loop (gram_fwd_pair.cuh).
+  const bool elected = elect_one();
 
-  if (warp == 0) {
-    // =========================== TMA producer: this CTA's NT/2 columns of F ===========================
-    uint32_t stage = 0, phase = 0;
-    for (int u = pair; u < p.total_units; u += npairs) {
-      const GramBwdPairUnit w = gbp_decode(p, u);
-      const int x0 = w.ht * p.NT + (int)rank * (p.NT / 2);
-      for (int kc = 0; kc < p.nkc; ++kc) {
-        mbar_wait(bar_empty + 8 * stage, phase ^ 1u, 100u + stage);
-        if (lane == 0) {
-          if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, 2u * (uint32_t)na * kAtomBytesB);
-          const uint32_t b_tile = smem_base + stage * kBpStageBytes + kBpTileBytes;
+  if (warp == 0 || warp == kBpProducer2Warp) {
+    // =========================== TMA producers: this CTA's NT/2 columns of F ===========================
+    // Two warps, even and odd K chunks (even and odd B stages): per chunk a producer spends a few hundred cycles on
+    // the mbarrier round trip and on issuing 3-4 tile loads, about as long as the chunk's MMAs take to execute.
+    const uint32_t pidx = (warp == 0) ? 0u : 1u;
+    if (elected) {
+      uint32_t n = 0;
+      const uint32_t tx_bytes = 2u * (uint32_t)na * kAtomBytesB;
+      for (int u = pair; u < p.total_units; u += npairs) {
+        const GramBwdPairUnit w = gbp_decode(p, u);
+        const int x0 = w.ht * p.NT + (int)rank * (p.NT / 2);
+        for (int kc = 0; kc < p.nkc; ++kc, ++n) {
+          if ((n & 1u) != pidx) continue;
+          const uint32_t stage = n % (uint32_t)kBpBStages, phase = (n / (uint32_t)kBpBStages) & 1u;
+          mbar_wait(bar_emptyB + 8 * stage, phase ^ 1u, 100u + stage);
+          if (rank == 0) mbar_arrive_expect_tx(bar_fullB + 8 * stage, tx_bytes);
+          const uint32_t b_tile = b_ring + stage * kBpTileBytes;
           for (int j = 0; j < na; ++j)
-            tma_load_3d_pair(b_tile + (uint32_t)j * kAtomBytesB, &tmF, full_leader + 8 * stage, x0 + j * (int)KC,
+            tma_load_3d_pair(b_tile + (uint32_t)j * kAtomBytesB, &tmF, fullB_leader + 8 * stage, x0 + j * (int)KC,
                              kc * (int)KC, w.b);
         }
-        __syncwarp();
-        if (++stage == kBpStages) { stage = 0; phase ^= 1u; }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
-    // =========================== MMA issuer (leader CTA) ===========================
-    if (rank == 0) {
+    // =========================== MMA issuer (one thread of the leader CTA) ===========================
+    // The loop body is kept to a few dozen instructions: descriptors are a per-ring constant plus small increments
+    // (stage * 1024 and k-step * 2 / * 64|128 in 16 B units), a full chunk issues its four MMAs without bound checks.
+    // A single thread executes ~10 cycles per dependent instruction; at ~300 instructions per chunk (first version)
+    // the issuer, not the tensor pipe, set the pace of the C >= 512 stages.
+    if (rank == 0 && elected) {
       const uint32_t idesc = make_idesc(T::kFormat, 256, (uint32_t)p.NT, 0, 1);
-      uint32_t stage = 0, phase = 0, it = 0;
+      const uint64_t dA0 = make_smem_desc_sw128(a_ring);
+      const uint64_t dB0 = (KIND == KIND_TF32) ? make_smem_desc_sw128b32_mnmajor(b_ring, kAtomBytesB)
+                                               : make_smem_desc_sw128_mnmajor(b_ring, kAtomBytesB);
+      constexpr uint64_t kStageInc = kBpTileBytes >> 4, kAInc = 32u >> 4, kBInc = kStepBytesB >> 4;
+      const int full_chunks = p.C / (int)KC;
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
       for (int u = pair; u < p.total_units; u += npairs, ++it) {
         const uint32_t ab = it & 1u, use = it >> 1;
         mbar_wait_cl(bar_tempty + 8 * ab, (use & 1u) ^ 1u, 200u + ab);
         tc_fence_after_sync();
+        const uint32_t acc = tmem_base + ab * 256u;
         for (int kc = 0; kc < p.nkc; ++kc) {
-          mbar_wait_cl(bar_full + 8 * stage, phase, 300u + stage);
+          mbar_wait_cl(bar_fullA + 8 * sa, pa, 300u + sa);
+          mbar_wait_cl(bar_fullB + 8 * sb, pb, 320u + sb);
           tc_fence_after_sync();
-          if (lane == 0) {
-            const uint32_t a_tile = smem_base + stage * kBpStageBytes;
-            const uint32_t b_tile = a_tile + kBpTileBytes;
-#pragma unroll
+          const uint64_t da = dA0 + sa * kStageInc, db = dB0 + sb * kStageInc;
+          if (kc < full_chunks) {
+            umma2<KIND>(acc, da, db, idesc, kc != 0 ? 1u : 0u);
+            umma2<KIND>(acc, da + kAInc, db + kBInc, idesc, 1u);
+            umma2<KIND>(acc, da + 2 * kAInc, db + 2 * kBInc, idesc, 1u);
+            umma2<KIND>(acc, da + 3 * kAInc, db + 3 * kBInc, idesc, 1u);
+          } else {
             for (uint32_t ks = 0; ks < KC / T::kUmmaK; ++ks) {
               if ((int)(kc * KC + ks * T::kUmmaK) >= p.C) break;
-              const uint64_t db = (KIND == KIND_TF32) ? make_smem_desc_sw128b32_mnmajor(b_tile + ks * kStepBytesB, kAtomBytesB)
-                                                      : make_smem_desc_sw128_mnmajor(b_tile + ks * kStepBytesB, kAtomBytesB);
-              umma2<KIND>(tmem_base + ab * 256u, make_smem_desc_sw128(a_tile + ks * 32u), db, idesc, (uint32_t)kc | ks);
+              umma2<KIND>(acc, da + ks * kAInc, db + ks * kBInc, idesc, (uint32_t)kc | ks);
             }
-            umma_commit2(bar_empty + 8 * stage);
-            if (kc + 1 == p.nkc) umma_commit2(bar_tfull + 8 * ab);
           }
-          __syncwarp();
-          if (++stage == kBpStages) { stage = 0; phase ^= 1u; }
+          umma_commit2(bar_emptyA + 8 * sa);
+          umma_commit2(bar_emptyB + 8 * sb);
+          if (kc + 1 == p.nkc) umma_commit2(bar_tfull + 8 * ab);
+          if (++sa == kBpAStages) { sa = 0; pa ^= 1u; }
+          if (++sb == kBpBStages) { sb = 0; pb ^= 1u; }
         }
       }
     }
+    __syncwarp();
   } else if (warp < 6) {
     // =========================== epilogue: TMEM -> scale -> staging -> TMA store ===========================
     const int q = warp & 3;                                 // TMEM lane quarter this warp may read
@@ -184,7 +232,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
         if (x >= p.HW) break;                               // warp-uniform
         float v[32];
         tmem_ld32(taddr + (uint32_t)n0, v);
-        if (lane == 0) tma_store_wait_read<kBpStoreBufs - 1>();   // the staging tile about to be reused has been read
+        if (elected) tma_store_wait_read<kBpStoreBufs - 1>();     // the staging tile about to be reused has been read
         __syncwarp();
         const uint32_t tile = my_store + buf * 4096u + (uint32_t)lane * kRowBytes;
 #pragma unroll
@@ -194,7 +242,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
                  __float_as_uint(v[4 * j + 3] * p.scale));
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0 && crow0 < p.C) {
+        if (elected && crow0 < p.C) {
           tma_store_3d(&tmD, my_store + buf * 4096u, x, crow0, w.b);
           tma_store_commit();
         }
@@ -204,56 +252,57 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_leader + 8 * ab);
     }
-    if (lane == 0) tma_store_wait_all<0>();
+    if (elected) tma_store_wait_all<0>();
     __syncwarp();
   } else {
     // =========================== A-tile generators: this CTA's 128 rows of M ===========================
-    // Group grp fills stage grp, i.e. the K chunks n = unit_index * nkc + kc with n % 4 == grp. Thread = A row.
+    // Group grp fills A stage grp, i.e. the K chunks n = unit_index * nkc + kc with n % 4 == grp. Thread = A row.
     // POOL: every 16 B chunk of the row is one value of the per-image table sym = dP + dP^T repeated (the pooling
-    // factor k is >= the elements of a chunk): 8 shared loads, 8 conversions and 8 16 B stores per K chunk. Each
-    // group keeps its own copy of the table; the NEXT unit's is fetched into registers while the current unit is
-    // generated and published through the group's second buffer.
+    // factor k is >= the elements of a chunk): 8 shared loads, 8 conversions and 8 16 B stores per K chunk. The
+    // table of the NEXT unit's image is fetched into registers (all 512 generator threads share the work) while the
+    // current unit is generated, and published through the second table buffer at the unit boundary.
     constexpr int EPC = 16 / (int)T::kElemBytes;            // elements per 16 B chunk: 4 (tf32) / 8 (bf16)
-    constexpr int NE = kBpMaxG * kBpMaxG / kBpGroupThreads; // table entries per thread
-    const int grp = (warp - 6) >> 2;
-    const int gt = threadIdx.x - 6 * 32 - grp * kBpGroupThreads;   // 0..127 = A row
+    constexpr int NE = kBpMaxG * kBpMaxG / kBpGenThreads;   // table entries per generator thread
+    const int grp = (warp - 6) / (kBpGroupThreads / 32);
+    const int gall = threadIdx.x - 6 * 32;                  // 0..511 among all generator threads
+    const int gt = gall - grp * kBpGroupThreads;            // 0..127 = A row
     const uint32_t row = (uint32_t)gt, sw = row & 7u;
     const uint32_t row_off = (row >> 3) * kAtomBytes + sw * kRowBytes;
     const int gg = p.g * p.g;
-    float* table = sym + grp * 2 * kBpTableFloats;
-    float pre[NE];
-    auto fetch_table = [&](int b) {
+    float* table = sym;
+    float pre_a[NE], pre_b[NE];                             // dP[i][j] and dP[j][i]: added only when published, so the
+    auto fetch_table = [&](int b) {                         // loads stay in flight while the current unit is generated
       const float* dp = p.dP + (long long)b * p.dp_img_stride;
 #pragma unroll
       for (int e = 0; e < NE; ++e) {
-        const int i = gt + e * kBpGroupThreads;
-        pre[e] = 0.f;
+        const int i = gall + e * kBpGenThreads;
+        pre_a[e] = 0.f;
+        pre_b[e] = 0.f;
         if (i < gg) {
           const int r = i / p.g, cc = i - r * p.g;
-          pre[e] = __ldg(dp + i) + __ldg(dp + cc * p.g + r);
+          pre_a[e] = __ldg(dp + i);
+          pre_b[e] = __ldg(dp + cc * p.g + r);
         }
       }
     };
     auto publish_table = [&](int which) {
 #pragma unroll
       for (int e = 0; e < NE; ++e) {
-        const int i = gt + e * kBpGroupThreads;
-        if (i < gg) table[which * kBpTableFloats + i] = pre[e];
+        const int i = gall + e * kBpGenThreads;
+        if (i < gg) table[which * kBpTableFloats + i] = pre_a[e] + pre_b[e];
       }
     };
-    uint32_t phase = 0;
     int cur = 0;
-    const uint32_t bar_id = 1u + (uint32_t)grp;
     if (MODE == GRAM_POOL) {
-      if (gt < kBpMaxG) {                                   // the zero rows
-        table[gg + gt] = 0.f;
-        table[kBpTableFloats + gg + gt] = 0.f;
+      if (gall < kBpMaxG) {                                 // the zero rows
+        table[gg + gall] = 0.f;
+        table[kBpTableFloats + gg + gall] = 0.f;
       }
       if (pair < p.total_units) {
         fetch_table(gbp_decode(p, pair).b);
         publish_table(0);
       }
-      named_bar_sync(bar_id, kBpGroupThreads);
+      named_bar_sync(1, kBpGenThreads);
     }
     int n0 = 0;                                             // sequence number of the unit's first K chunk
     for (int u = pair; u < p.total_units; u += npairs, n0 += p.nkc) {
@@ -264,8 +313,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
       const bool row_ok = c < p.C;
       const float* srow = table + cur * kBpTableFloats + (row_ok ? (c >> p.kshift) * p.g : gg);
       for (int kc = (grp - (n0 & 3) + 4) & 3; kc < p.nkc; kc += kBpGroups) {
-        mbar_wait(bar_empty + 8 * grp, phase ^ 1u, 500u + grp);
-        const uint32_t a_row = smem_base + (uint32_t)grp * kBpStageBytes + row_off;
+        const uint32_t n = (uint32_t)(n0 + kc);
+        const uint32_t stage = n % (uint32_t)kBpAStages, phase = (n / (uint32_t)kBpAStages) & 1u;
+        mbar_wait(bar_emptyA + 8 * stage, phase ^ 1u, 500u + stage);
+        const uint32_t a_row = a_ring + stage * kBpTileBytes + row_off;
         const int dbase = kc * (int)KC;
         if (MODE == GRAM_POOL) {
           const bool full_chunk = dbase + (int)KC <= p.C;
@@ -301,12 +352,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(full_leader + 8 * grp);
-        phase ^= 1u;
+        if (lane == 0) mbar_arrive_cluster(fullA_leader + 8 * stage);
       }
       if (MODE == GRAM_POOL) {
         if (has_next) publish_table(cur ^ 1);               // last read one unit ago, before the barrier that ended it
-        named_bar_sync(bar_id, kBpGroupThreads);            // the group sees the next table and is done with this one
+        named_bar_sync(1, kBpGenThreads);                   // every group sees the next table and is done with this one
         cur ^= 1;
       }
     }

@@ -384,7 +384,7 @@ __device__ __forceinline__ void gf_issue_unit(const GramFwdParams& p, const Gram
       mbar_wait(bar_full + 8 * sB, phaseB, 310u + sB);
     }
     tc_fence_after_sync();
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync, not a lane test: see gram_fwd_pair.cuh
       const uint32_t aI = smem_base + sA * kGfStageBytes;   // rows of block I
       const uint32_t aJ = smem_base + sB * kGfStageBytes;   // rows of block J (== I on the diagonal)
       const uint32_t acc = (kb > w.kb0) ? 1u : 0u;

@@ -97,57 +97,72 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFpThreads, 1)
 
   const uint32_t full_leader = mapa_u32(bar_full, 0);
   const uint32_t tempty_leader = mapa_u32(bar_tempty, 0);
+  // One thread per warp issues the TMA / tcgen05 instructions. It is chosen with elect.sync, not `lane == 0`: ptxas
+  // then knows the guarded region is single-threaded and feeds the instructions' uniform-register operands with plain
+  // R2UR / uniform-datapath arithmetic; with a lane test it wraps every UTCHMMA / UTMALDG in an elect-broadcast-retry
+  // loop (~150 cycles per instruction, which alone capped the tensor pipe at ~60 % in the first version).
+  const bool elected = elect_one();
 
   if (warp == 0) {
-    // =========================== TMA producer: this CTA's 128 rows of block I (and of block J) ===========================
-    uint32_t stage = 0, phase = 0;
-    for (int u = pair; u < p.total_units; u += npairs) {
-      const GramUnit w = gram_decode_unit(p, u);
-      const bool diag = (w.I == w.J);
-      const int rowA = w.I * 256 + (int)rank * 128, rowB = w.J * 256 + (int)rank * 128;
-      for (int kb = w.kb0; kb < w.kb1; ++kb) {
-        mbar_wait(bar_empty + 8 * stage, phase ^ 1u, 100u + stage);
-        if (lane == 0) {
-          if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, (diag ? 2u : 4u) * kFpTileBytes);
+    // =========================== TMA producer (one thread): this CTA's 128 rows of block I (and of block J) ==========
+    if (elected) {
+      uint32_t stage = 0, phase = 0;
+      for (int u = pair; u < p.total_units; u += npairs) {
+        const GramUnit w = gram_decode_unit(p, u);
+        const bool diag = (w.I == w.J);
+        const int rowA = w.I * 256 + (int)rank * 128, rowB = w.J * 256 + (int)rank * 128;
+        const uint32_t tx_bytes = (diag ? 2u : 4u) * kFpTileBytes;
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1u, 100u + stage);
+          if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, tx_bytes);
           const uint32_t a_tile = smem_base + stage * kFpStageBytes;
           tma_load_3d_pair(a_tile, &tmap, full_leader + 8 * stage, kb * KB, rowA, w.b);
           if (!diag) tma_load_3d_pair(a_tile + kFpTileBytes, &tmap, full_leader + 8 * stage, kb * KB, rowB, w.b);
-        }
-        __syncwarp();
-        if (++stage == kFpStages) { stage = 0; phase ^= 1u; }
-      }
-    }
-  } else if (warp == 1) {
-    // =========================== MMA issuer (leader CTA) ===========================
-    if (rank == 0) {
-      const uint32_t idesc = make_idesc(T::kFormat, 256, 256, 0, 0);
-      uint32_t stage = 0, phase = 0, it = 0;
-      for (int u = pair; u < p.total_units; u += npairs, ++it) {
-        const GramUnit w = gram_decode_unit(p, u);
-        const bool diag = (w.I == w.J);
-        const uint32_t ab = it & 1u, use = it >> 1;
-        mbar_wait_cl(bar_tempty + 8 * ab, (use & 1u) ^ 1u, 200u + ab);
-        tc_fence_after_sync();
-        for (int kb = w.kb0; kb < w.kb1; ++kb) {
-          mbar_wait_cl(bar_full + 8 * stage, phase, 300u + stage);
-          tc_fence_after_sync();
-          if (lane == 0) {
-            const uint32_t a_tile = smem_base + stage * kFpStageBytes;
-            const uint32_t b_tile = diag ? a_tile : a_tile + kFpTileBytes;
-#pragma unroll
-            for (uint32_t ks = 0; ks < T::kElemsPerRow / T::kUmmaK; ++ks) {
-              if ((int)(kb * KB + ks * T::kUmmaK) >= p.HW) break;     // K tail: whole k-steps past HW are skipped
-              umma2<KIND>(tmem_base + ab * 256u, make_smem_desc_sw128(a_tile + ks * 32u),
-                          make_smem_desc_sw128(b_tile + ks * 32u), idesc, (uint32_t)(kb - w.kb0) | ks);
-            }
-            umma_commit2(bar_empty + 8 * stage);
-            if (kb + 1 == w.kb1) umma_commit2(bar_tfull + 8 * ab);
-          }
-          __syncwarp();
           if (++stage == kFpStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
+    __syncwarp();
+  } else if (warp == 1) {
+    // =========================== MMA issuer (one thread of the leader CTA) ===========================
+    // Descriptors = a constant for stage 0 plus stage * 2048 and k-step * 2 (16 B units); a K block that lies fully
+    // inside HW issues its four MMAs without bound checks. Keeping this loop to a few dozen instructions matters: one
+    // thread executes ~10 cycles per dependent instruction and a K block's MMAs take only 512 cycles.
+    if (rank == 0 && elected) {
+      const uint32_t idesc = make_idesc(T::kFormat, 256, 256, 0, 0);
+      const uint64_t d0 = make_smem_desc_sw128(smem_base);
+      constexpr uint64_t kStageInc = kFpStageBytes >> 4, kTileInc = kFpTileBytes >> 4, kKInc = 32u >> 4;
+      const int full_kb = p.HW / KB;
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (int u = pair; u < p.total_units; u += npairs, ++it) {
+        const GramUnit w = gram_decode_unit(p, u);
+        const uint64_t b_off = (w.I == w.J) ? 0 : kTileInc;
+        const uint32_t ab = it & 1u, use = it >> 1;
+        mbar_wait_cl(bar_tempty + 8 * ab, (use & 1u) ^ 1u, 200u + ab);
+        tc_fence_after_sync();
+        const uint32_t acc = tmem_base + ab * 256u;
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
+          mbar_wait_cl(bar_full + 8 * stage, phase, 300u + stage);
+          tc_fence_after_sync();
+          const uint64_t da = d0 + stage * kStageInc, db = da + b_off;
+          if (kb < full_kb) {
+            umma2<KIND>(acc, da, db, idesc, kb != w.kb0 ? 1u : 0u);
+            umma2<KIND>(acc, da + kKInc, db + kKInc, idesc, 1u);
+            umma2<KIND>(acc, da + 2 * kKInc, db + 2 * kKInc, idesc, 1u);
+            umma2<KIND>(acc, da + 3 * kKInc, db + 3 * kKInc, idesc, 1u);
+          } else {
+            for (uint32_t ks = 0; ks < T::kElemsPerRow / T::kUmmaK; ++ks) {
+              if ((int)(kb * KB + ks * T::kUmmaK) >= p.HW) break;     // K tail: whole k-steps past HW are skipped
+              umma2<KIND>(acc, da + ks * kKInc, db + ks * kKInc, idesc, (uint32_t)(kb - w.kb0) | ks);
+            }
+          }
+          umma_commit2(bar_empty + 8 * stage);
+          if (kb + 1 == w.kb1) umma_commit2(bar_tfull + 8 * ab);
+          if (++stage == kFpStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
   } else {
     // =========================== epilogue ===========================
     const int q = warp & 3;

@@ -110,6 +110,7 @@ static cudaError_t launch_gram_fwd_kp(const GramFwdParams& p, int kp, int grid, 
 // Pair (cta_group::2, TMA-staged) kernels. -1 = auto, 0 = never, 1 = whenever TMA can describe the tensors.
 static int g_opt_fwd_pair = -1;
 static int g_opt_bwd_pair = -1;
+static int g_opt_bwd_nt = 0;        // 0 = plan the x-tile width; 64..256 (multiple of 32) forces it (experiments)
 static int g_opt_tma_f32_type = 1;  // tensor-map data type for fp32 features: 0 = FLOAT32, 1 = TFLOAT32
 
 template <int KIND, int KP>
@@ -259,6 +260,7 @@ static int gram_bwd_common(const void* F, int f_dtype, long long img_stride, lon
       q.dP = dP; q.dp_img_stride = dp_img_stride; q.g = g; q.kshift = p.kshift; q.dG = dG;
       q.scale = p.scale;
       gbp_plan_tiles(HW, &q.NT, &q.nHT);
+      if (g_opt_bwd_nt) { q.NT = g_opt_bwd_nt; q.nHT = (HW + q.NT - 1) / q.NT; }
       q.nCB = (C + 255) / 256;
       q.nkc = (C + kc_elems - 1) / kc_elems;
       const long long tot = (long long)B * q.nHT * q.nCB;
@@ -432,6 +434,11 @@ int gh_set_option(const char* name, int value) {
   if (key == "gram_bwd_pair") {
     if (value < -1 || value > 1) return GH_ERR_BAD_ARG;
     g_opt_bwd_pair = value;
+    return 0;
+  }
+  if (key == "gram_bwd_nt") {
+    if (value != 0 && (value < 64 || value > 256 || value % 32)) return GH_ERR_BAD_ARG;
+    g_opt_bwd_nt = value;
     return 0;
   }
   if (key == "tma_f32_type") {

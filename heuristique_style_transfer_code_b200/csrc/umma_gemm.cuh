@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(kUgThreads, 1) umma_gemm_kernel(const UmmaGemm
       for (int kb = u.kb0; kb < u.kb1; ++kb) {
         mbar_wait(bar_full + 8 * stage, phase, 300u + stage);
         tc_fence_after_sync();
-        if (lane == 0) {
+        if (elect_one()) {   // elect.sync, not a lane test: see gram_fwd_pair.cuh
           const uint32_t a_hi = smem_base + stage * kUgStageBytes, a_lo = a_hi + kUgATile;
           const uint32_t b_hi = a_hi + 2 * kUgATile, b_lo = b_hi + kUgBTile;
 #pragma unroll
