@@ -322,12 +322,12 @@ def run_ours(args):
 
     line = {"metric": "images/sec", "value": round(value, 1), "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16/tf32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": total, "per_gpu_batch": B, "image": IMAGE,
                        "truncate_layer": TRUNC, "gram_matrix_size": GRAM_SIZE, "num_classes": NUM_CLASSES,
-                       "precision": "encoder: cuDNN fp32 (TF32 conv allowed, torch default); Gram (tcgen05, fp32 accumulate): "
-                                    "C=256 stage bf16 operands (cvt.rn in the producers), C>=512 stages tf32 operands "
-                                    "(TMA TFLOAT32 round-to-nearest); attention/classifier: split-bf16 x3 (fp32-accurate)",
+                       "precision": "encoder: cuDNN fp32 (TF32 conv allowed, torch default); Gram forward and backward (tcgen05, "
+                                    "fp32 accumulate): tf32 operands, rounded to nearest by the TMA unit (TFLOAT32 tensor "
+                                    "maps); attention/classifier: split-bf16 x3 (fp32-accurate)",
                        "l2_policy": "inputs larger than L2 (154 MB images, 210/105/51 MB stage activations per step)",
                        "parallelism": f"batch-sharded x{world}, all_gather of logits+embeddings" if world > 1 else "single GPU"},
             "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -166,7 +166,9 @@ static int gram_fwd_common(const void* F, int f_dtype, long long img_stride, lon
 
   // ---- CTA-pair kernel with TMA-staged operands (bf16 -> kind::f16, fp32 -> kind::tf32) ----
   const bool is_bf16 = (f_dtype == GH_DTYPE_BF16);
-  const bool want_pair = g_opt_fwd_pair == 1 || (g_opt_fwd_pair == -1 && (is_bf16 || C >= 512));
+  // auto: whenever TMA can describe the tensor. At C = 256 / fp32 the two families tie at batch 256 (143 us) and the
+  // pair kernel wins at larger batches; its tf32 operands are also ~10x closer to fp32 than the ldg kernel's bf16.
+  const bool want_pair = g_opt_fwd_pair != 0;
   if (want_pair && sms >= 2) {
     CUtensorMap map;
     const int kb_elems = is_bf16 ? 64 : 32;
