@@ -268,6 +268,23 @@ def run_ours(args):
     h2d = B * 3 * IMAGE * IMAGE * 4
     d2h = total * (GRAM_SIZE * GRAM_SIZE + NUM_CLASSES) * 4
 
+    # ---- opt-in backbone hand-off: encoder under bf16 autocast, channels_last; same batch, device resident.
+    # Reported beside the headline, never as it: it changes the numerics of the cuDNN backbone (not of the head).
+    handoff = None
+    if not args.skip_handoff:
+        model.set_backbone_mode("bf16_channels_last")
+        for _ in range(3):
+            infer_step()
+        hms = timed_region(infer_step, args.steps, device, D)
+        with torch.no_grad():
+            _, lg_fast = model(x)
+            model.set_backbone_mode("reference")
+            _, lg_ref = model(x)
+        handoff = {"mode": "bf16_channels_last", "value": round(total * args.steps / (hms / 1e3), 1), "unit": "images/s",
+                   "ms_per_step": round(hms / args.steps, 3),
+                   "logits_rel_diff_vs_fp32_backbone": float((lg_fast.float() - lg_ref).norm() / lg_ref.norm()),
+                   "argmax_equal": bool((lg_fast.argmax(1) == lg_ref.argmax(1)).all())}
+
     # ---- configs[2]: training step, global batch 512 over the ranks (strong scaling), AdamW ----
     train = None
     if not args.skip_train:
@@ -338,6 +355,7 @@ def run_ours(args):
             "clocks": clocks.summary(),
             "breakdown": {"encoder_cudnn_ms": round(enc_ms, 3), "head_ms": round(head_ms, 3),
                           "head_images_per_s": round(B / (head_ms / 1e3), 1), "kernels": kernels},
+            "backbone_handoff": handoff,
             "train": train}
     print(json.dumps(line), flush=True)
 
@@ -353,6 +371,7 @@ def main():
     ap.add_argument("--train-steps", type=int, default=10)
     ap.add_argument("--skip-train", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-handoff", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

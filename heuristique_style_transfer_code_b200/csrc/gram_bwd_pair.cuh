@@ -15,9 +15,9 @@
 //   epilogue: tcgen05.ld (lane = channel, 32 positions) -> *scale -> swizzled staging tile -> TMA store, so the
 //             4 B/element gradient leaves the SM as full 128 B lines without occupying the LSU
 // Warps: 0 and 22 = TMA producers (even / odd K chunks), 1 = TMEM owner + MMA issuer (leader CTA only), 2-5 = epilogue,
-// 6-21 = A-tile generators in four groups of four warps; group i owns A-ring stage i, so four K chunks are generated
-// concurrently and the per-chunk handshake (mbarrier wait, proxy fence, arrive) of one group overlaps the stores of
-// the others. A and B tiles travel in separate rings: 5 stages of generated A, 5 stages (80 KB) of TMA-loaded F, 3 store
+// 6-21 = A-tile generators in four groups of four warps; group i generates the K chunks n = i mod 4 (into A-ring stage
+// n mod 5), so four chunks are generated concurrently and the per-chunk handshake (mbarrier wait, proxy fence, arrive)
+// of one group overlaps the stores of the others. A and B tiles travel in separate rings: 5 stages of generated A, 5 stages (80 KB) of TMA-loaded F, 3 store
 // staging tiles per epilogue warp -- the best of the depth sweep in profiles/ (6 B stages are faster for C >= 512 but
 // 20 % slower on the HBM-bound C = 256 stage).
 #pragma once

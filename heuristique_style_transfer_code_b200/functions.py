@@ -238,37 +238,97 @@ def _save_side_by_side(path, image):
         Image.fromarray((np.clip(image, 0, 1) * 255).astype(np.uint8)).save(path)
 
 
+class _StyleIteration:
+    """One optimisation step of style_transfer() -- encoder forward, dense Gram, MSE against the target Gram, backward
+    to the image, Adam step -- captured once in a CUDA graph and replayed.
+
+    At batch 1 the step is ~400 small kernels (cuDNN encoder forward + backward, the dense tcgen05 Gram forward and
+    backward, the loss, Adam) and is bound by launch latency, not by any kernel; replaying it as one graph removes
+    that. The image, the target Gram and the optimiser state live in static buffers: a new image only copies into them.
+    The arithmetic and its order are the eager loop's (reference functions/...:283-299)."""
+
+    def __init__(self, model, encoder, device, learning_rate, use_graph=True):
+        self.model, self.encoder, self.device = model, encoder, torch.device(device)
+        self.noise = torch.zeros((1, 3, 224, 224), device=self.device, requires_grad=True)
+        self.use_graph = bool(use_graph) and self.device.type == 'cuda'
+        self.optimizer = torch.optim.Adam([self.noise], lr=learning_rate, capturable=self.use_graph)
+        self.mse = nn.MSELoss()
+        self.target = None
+        self.loss = None
+        self.graph = None
+
+    def _step(self):
+        loss = self.mse(self.model.gram_matrix(self.encoder(self.noise)), self.target)
+        loss.backward()
+        self.optimizer.step()
+        return loss
+
+    def _reset_optimizer(self):
+        for state in self.optimizer.state.values():
+            for v in state.values():
+                if torch.is_tensor(v):
+                    v.zero_()
+
+    def start(self, target, noise_init):
+        """New image: target Gram and a fresh noise image; Adam restarts from zero moments (a new optimiser upstream)."""
+        if self.target is None:
+            self.target = target.detach().clone()
+        else:
+            self.target.copy_(target)
+        if self.use_graph and self.graph is None:
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):                     # warm-up off the capture stream (allocations, cuDNN plans)
+                for _ in range(3):
+                    self.optimizer.zero_grad(set_to_none=True)
+                    self._step()
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            self.optimizer.zero_grad(set_to_none=True)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.loss = self._step()
+        with torch.no_grad():
+            self.noise.copy_(noise_init)
+        self._reset_optimizer()
+
+    def step(self):
+        """Runs one iteration and returns the loss as a Python float (the only synchronisation, as upstream)."""
+        if self.graph is not None:
+            self.graph.replay()
+            return self.loss.item()
+        self.optimizer.zero_grad()
+        return self._step().item()
+
+
 def style_transfer(model, data_loader, device, save_dir, layers=None, threshold=1e-4, num_iterations=500,
-                   learning_rate=0.01):
+                   learning_rate=0.01, use_graph=True):
     """For every image: optimise a noise image with Adam so that the dense Gram of the first `layers` encoder children
     matches the image's (MSE), stop below `threshold`, save original|result under save_dir/style_transfer_<date>/<label>
     (:247-314). Both Gram evaluations and the gradient through them go through model.gram_matrix(), i.e. the dense
-    tcgen05 forward/backward kernels."""
+    tcgen05 forward/backward kernels; on a CUDA device the whole iteration is replayed from one CUDA graph
+    (`use_graph=False` runs the eager loop, same arithmetic)."""
     model.eval()
     out_root = os.path.join(save_dir, f'style_transfer_{datetime.now().strftime("%Y-%m-%d")}')
     os.makedirs(out_root, exist_ok=True)
-    mse = nn.MSELoss()
     mean = torch.tensor([0.485, 0.456, 0.406], device=device)
     std = torch.tensor([0.229, 0.224, 0.225], device=device)
+    encoder = nn.Sequential(*list(model.truncated_encoder.children())[:layers]).to(device)
+    runner = _StyleIteration(model, encoder, device, learning_rate, use_graph=use_graph)
     for inputs, labels in data_loader:
         inputs, labels = inputs.to(device), labels.to(device)
         for i, image in enumerate(inputs):
             image = image.unsqueeze(0)
-            encoder = nn.Sequential(*list(model.truncated_encoder.children())[:layers]).to(device)
             with torch.no_grad():
                 target = model.gram_matrix(encoder(image))
             class_dir = os.path.join(out_root, str(labels[i].item()))
             os.makedirs(class_dir, exist_ok=True)
-            noise = torch.randn((1, 3, 224, 224), device=device, requires_grad=True)
-            optimizer = torch.optim.Adam([noise], lr=learning_rate)
+            runner.start(target, torch.randn((1, 3, 224, 224), device=device))
             for iteration in range(num_iterations):
-                optimizer.zero_grad()
-                loss = mse(model.gram_matrix(encoder(noise)), target)
-                loss.backward()
-                optimizer.step()
-                if loss.item() < threshold:
+                if runner.step() < threshold:
                     print(f"Seuil atteint pour l'image {i}, itération {iteration}")
                     break
+            noise = runner.noise
             result = denormalize(noise.detach().cpu().squeeze(), mean, std).clamp_(0, 1).numpy().transpose(1, 2, 0)
             original = denormalize(image.detach().cpu().squeeze(), mean, std).clamp_(0, 1).numpy().transpose(1, 2, 0)
             save_path = os.path.join(class_dir, f'style_transfer_{i}.png')

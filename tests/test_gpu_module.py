@@ -199,3 +199,33 @@ def test_backbone_modes_agree_with_the_reference_mode():
         assert rel <= 3e-2 and grel <= 1e-1, (mode, rel, grel)      # bf16 backbone: ~1e-2 on activations
     with pytest.raises(ValueError):
         model.set_backbone_mode("fp8")
+
+
+def test_style_iteration_graph_matches_eager():
+    """functions._StyleIteration: the CUDA-graph replay of one style-transfer step against the eager loop."""
+    import torch
+    from torchvision import models
+    from heuristique_style_transfer_code_b200 import TruncatedResNet50_for_test
+    from heuristique_style_transfer_code_b200.functions import _StyleIteration
+    torch.manual_seed(0)
+    model = TruncatedResNet50_for_test(models.resnet50(weights=None), 7, 4, 32, device="cuda:0").eval()
+    encoder = torch.nn.Sequential(*list(model.truncated_encoder.children())[:5]).to("cuda:0")
+    image = torch.randn(1, 3, 224, 224, device="cuda:0")
+    with torch.no_grad():
+        target = model.gram_matrix(encoder(image))
+    noise0 = torch.randn(1, 3, 224, 224, device="cuda:0")
+    runs = {}
+    for use_graph in (False, True):
+        it = _StyleIteration(model, encoder, "cuda:0", 0.01, use_graph=use_graph)
+        losses = []
+        for rep in range(2):                      # second image reuses the captured graph and restarts Adam
+            it.start(target, noise0)
+            losses.append([it.step() for _ in range(6)])
+        assert (it.graph is not None) == use_graph
+        runs[use_graph] = (losses, it.noise.detach().clone())
+    (le, ne), (lg, ng) = runs[False], runs[True]
+    for a, b in zip(le[0] + le[1], lg[0] + lg[1]):
+        assert abs(a - b) <= 2e-3 * abs(a), (le, lg)
+    assert le[0][0] > le[0][-1]                   # the loss goes down
+    assert all(abs(a - b) <= 2e-3 * abs(a) for a, b in zip(le[0], le[1]))   # restart reproduces the first run
+    assert float((ne - ng).abs().max()) <= 5e-3
