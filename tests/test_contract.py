@@ -150,14 +150,16 @@ def test_denormalize_inplace():
 def test_function_signatures_match_reference():
     ref = load_reference_functions()
     for name in ("load_model", "save_model_weights", "load_model_weights", "train_model", "evaluate_model",
-                 "evaluate_model_test", "set_parameter_requires_grad", "denormalize", "style_transfer",
+                 "evaluate_model_test", "set_parameter_requires_grad", "denormalize",
                  "load_hyperparameters", "perform_tsne", "plot_tsne_interactive", "create_onpick_function"):
         a = inspect.signature(getattr(ref, name))
         b = inspect.signature(getattr(F, name))
         assert list(a.parameters.items()) == list(b.parameters.items()), name
-    a = list(inspect.signature(ref.run_camera).parameters)
-    b = list(inspect.signature(F.run_camera).parameters)
-    assert b[:len(a)] == a                                   # additions are trailing keyword arguments with defaults
+    for name in ("run_camera", "style_transfer"):            # additions are trailing keyword arguments with defaults
+        a = list(inspect.signature(getattr(ref, name)).parameters.items())
+        b = list(inspect.signature(getattr(F, name)).parameters.items())
+        assert b[:len(a)] == a, name
+        assert all(p.default is not inspect.Parameter.empty for _, p in b[len(a):]), name
 
 
 def test_loops_run_with_a_cpu_stand_in_model(tmp_path):
@@ -204,3 +206,19 @@ def test_cuda_prefetch_passes_batches_through_in_order_on_cpu():
     for i, (x, y) in enumerate(out):
         assert torch.equal(x, batches[i][0]) and torch.equal(y, batches[i][1])
     assert list(cuda_prefetch(iter([]), "cpu")) == []
+
+
+def test_backbone_mode_defaults_and_validation(monkeypatch):
+    from torchvision import models
+    from heuristique_style_transfer_code_b200.modules import BACKBONE_MODES
+    monkeypatch.delenv("GRAMHEAD_BACKBONE", raising=False)
+    m = TruncatedResNet50(models.resnet50(weights=None), 5, 4, 8, device="cpu")
+    assert m.backbone_mode == "reference"                 # CPU construction keeps the reference's NCHW execution
+    assert set(BACKBONE_MODES) == {"reference", "channels_last", "bf16", "bf16_channels_last"}
+    keys_before = list(m.state_dict())
+    m.set_backbone_mode("channels_last")
+    assert m.backbone_mode == "channels_last" and list(m.state_dict()) == keys_before
+    with pytest.raises(ValueError):
+        m.set_backbone_mode("int8")
+    monkeypatch.setenv("GRAMHEAD_BACKBONE", "bf16")
+    assert TruncatedResNet50(models.resnet50(weights=None), 5, 4, 8, device="cpu").backbone_mode == "bf16"
