@@ -88,7 +88,11 @@ __device__ __forceinline__ uint32_t f32_to_tf32_rna(float x) {
 }
 
 // MODE: GRAM_POOL (A generated from the g x g descriptor gradient) or GRAM_DENSE (A = dG + dG^T read from HBM).
-template <int KIND, int MODE>
+// NHWC = false: F and dF with x contiguous (NCHW): F is the MN-major B operand, dF leaves as [channel rows][32 x] tiles.
+// NHWC = true : channels_last F and dF (c contiguous): F[d][x] at x*C + d is K-contiguous, i.e. a K-major B operand
+//               [NT/2 position rows][128 B of input channels] fetched by ONE box per chunk; the epilogue transposes
+//               through the staging tile ([32 x rows][32 channels]) so that dF is stored NHWC too.
+template <int KIND, int MODE, bool NHWC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
     gram_bwd_pair_kernel(const GramBwdPairParams p, const __grid_constant__ CUtensorMap tmF,
                          const __grid_constant__ CUtensorMap tmD) {
@@ -153,7 +157,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
     const uint32_t pidx = (warp == 0) ? 0u : 1u;
     if (elected) {
       uint32_t n = 0;
-      const uint32_t tx_bytes = 2u * (uint32_t)na * kAtomBytesB;
+      const uint32_t tx_bytes = NHWC ? 2u * (uint32_t)(p.NT / 2) * kRowBytes : 2u * (uint32_t)na * kAtomBytesB;
       for (int u = pair; u < p.total_units; u += npairs) {
         const GramBwdPairUnit w = gbp_decode(p, u);
         const int x0 = w.ht * p.NT + (int)rank * (p.NT / 2);
@@ -163,9 +167,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
           mbar_wait(bar_emptyB + 8 * stage, phase ^ 1u, 100u + stage);
           if (rank == 0) mbar_arrive_expect_tx(bar_fullB + 8 * stage, tx_bytes);
           const uint32_t b_tile = b_ring + stage * kBpTileBytes;
-          for (int j = 0; j < na; ++j)
-            tma_load_3d_pair(b_tile + (uint32_t)j * kAtomBytesB, &tmF, fullB_leader + 8 * stage, x0 + j * (int)KC,
-                             kc * (int)KC, w.b);
+          if constexpr (NHWC) {
+            tma_load_3d_pair(b_tile, &tmF, fullB_leader + 8 * stage, kc * (int)KC, x0, w.b);
+          } else {
+            for (int j = 0; j < na; ++j)
+              tma_load_3d_pair(b_tile + (uint32_t)j * kAtomBytesB, &tmF, fullB_leader + 8 * stage, x0 + j * (int)KC,
+                               kc * (int)KC, w.b);
+          }
         }
       }
     }
@@ -177,11 +185,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
     // A single thread executes ~10 cycles per dependent instruction; at ~300 instructions per chunk (first version)
     // the issuer, not the tensor pipe, set the pace of the C >= 512 stages.
     if (rank == 0 && elected) {
-      const uint32_t idesc = make_idesc(T::kFormat, 256, (uint32_t)p.NT, 0, 1);
+      const uint32_t idesc = make_idesc(T::kFormat, 256, (uint32_t)p.NT, 0, NHWC ? 0 : 1);
       const uint64_t dA0 = make_smem_desc_sw128(a_ring);
-      const uint64_t dB0 = (KIND == KIND_TF32) ? make_smem_desc_sw128b32_mnmajor(b_ring, kAtomBytesB)
-                                               : make_smem_desc_sw128_mnmajor(b_ring, kAtomBytesB);
-      constexpr uint64_t kStageInc = kBpTileBytes >> 4, kAInc = 32u >> 4, kBInc = kStepBytesB >> 4;
+      const uint64_t dB0 = NHWC ? make_smem_desc_sw128(b_ring)
+                                : (KIND == KIND_TF32 ? make_smem_desc_sw128b32_mnmajor(b_ring, kAtomBytesB)
+                                                     : make_smem_desc_sw128_mnmajor(b_ring, kAtomBytesB));
+      constexpr uint64_t kStageInc = kBpTileBytes >> 4, kAInc = 32u >> 4, kBInc = NHWC ? 32u >> 4 : kStepBytesB >> 4;
       const int full_chunks = p.C / (int)KC;
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
       for (int u = pair; u < p.total_units; u += npairs, ++it) {
@@ -234,16 +243,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
         tmem_ld32(taddr + (uint32_t)n0, v);
         if (elected) tma_store_wait_read<kBpStoreBufs - 1>();     // the staging tile about to be reused has been read
         __syncwarp();
-        const uint32_t tile = my_store + buf * 4096u + (uint32_t)lane * kRowBytes;
+        if constexpr (NHWC) {
+          // staging tile = [32 x rows][32 channels]: lane (= channel) writes column `lane` of every row; one row is 32
+          // consecutive words across the warp (16 B chunks XOR-swizzled by the row), so the stores are conflict-free
+          const uint32_t tile = my_store + buf * 4096u + (((uint32_t)lane & 3u) << 2);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          sts_u4(tile + ((((uint32_t)j) ^ ((uint32_t)lane & 7u)) << 4), __float_as_uint(v[4 * j] * p.scale),
-                 __float_as_uint(v[4 * j + 1] * p.scale), __float_as_uint(v[4 * j + 2] * p.scale),
-                 __float_as_uint(v[4 * j + 3] * p.scale));
+          for (int j = 0; j < 32; ++j) {
+            const uint32_t addr = tile + (uint32_t)j * kRowBytes + (((((uint32_t)lane >> 2) ^ ((uint32_t)j & 7u))) << 4);
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(__float_as_uint(v[j] * p.scale)) : "memory");
+          }
+        } else {
+          const uint32_t tile = my_store + buf * 4096u + (uint32_t)lane * kRowBytes;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            sts_u4(tile + ((((uint32_t)j) ^ ((uint32_t)lane & 7u)) << 4), __float_as_uint(v[4 * j] * p.scale),
+                   __float_as_uint(v[4 * j + 1] * p.scale), __float_as_uint(v[4 * j + 2] * p.scale),
+                   __float_as_uint(v[4 * j + 3] * p.scale));
+        }
         fence_proxy_async_smem();
         __syncwarp();
         if (elected && crow0 < p.C) {
-          tma_store_3d(&tmD, my_store + buf * 4096u, x, crow0, w.b);
+          if constexpr (NHWC) tma_store_3d(&tmD, my_store + buf * 4096u, crow0, x, w.b);
+          else tma_store_3d(&tmD, my_store + buf * 4096u, x, crow0, w.b);
           tma_store_commit();
         }
         buf = (buf + 1u) % kBpStoreBufs;

@@ -59,11 +59,16 @@ __device__ __forceinline__ void gfp_epilogue_unit(const GramFwdParams& p, const 
 }
 
 // p.nkb counts K blocks of KindTraits<KIND>::kElemsPerRow positions (64 for bf16, 32 for fp32/tf32).
-template <int KIND, int KP>
+// NHWC = false: features with x contiguous (NCHW): K-major operand tiles, 3-D map (x, c, b), one 128-row box per tile.
+// NHWC = true : channels_last features (c contiguous): the same 128 channels x KB positions arrive as MN-major tiles
+//               ([atom][KB positions][128 B of channels]) through ONE 4-D box per tile (make_tensor_map_nhwc_mn); only
+//               the producer's coordinates and the descriptors differ, the accumulators and the epilogue are the same.
+template <int KIND, int KP, bool NHWC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFpThreads, 1)
     gram_fwd_pair_kernel(const GramFwdParams p, const __grid_constant__ CUtensorMap tmap) {
   using T = KindTraits<KIND>;
   constexpr int KB = (int)T::kElemsPerRow;
+  constexpr int E = (int)T::kElemsPerRow;                          // channels per 128 B atom (NHWC)
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -116,8 +121,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFpThreads, 1)
           mbar_wait(bar_empty + 8 * stage, phase ^ 1u, 100u + stage);
           if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, tx_bytes);
           const uint32_t a_tile = smem_base + stage * kFpStageBytes;
-          tma_load_3d_pair(a_tile, &tmap, full_leader + 8 * stage, kb * KB, rowA, w.b);
-          if (!diag) tma_load_3d_pair(a_tile + kFpTileBytes, &tmap, full_leader + 8 * stage, kb * KB, rowB, w.b);
+          if constexpr (NHWC) {
+            tma_load_4d_pair(a_tile, &tmap, full_leader + 8 * stage, 0, kb * KB, rowA / E, w.b);
+            if (!diag) tma_load_4d_pair(a_tile + kFpTileBytes, &tmap, full_leader + 8 * stage, 0, kb * KB, rowB / E, w.b);
+          } else {
+            tma_load_3d_pair(a_tile, &tmap, full_leader + 8 * stage, kb * KB, rowA, w.b);
+            if (!diag) tma_load_3d_pair(a_tile + kFpTileBytes, &tmap, full_leader + 8 * stage, kb * KB, rowB, w.b);
+          }
           if (++stage == kFpStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -129,9 +139,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFpThreads, 1)
     // inside HW issues its four MMAs without bound checks. Keeping this loop to a few dozen instructions matters: one
     // thread executes ~10 cycles per dependent instruction and a K block's MMAs take only 512 cycles.
     if (rank == 0 && elected) {
-      const uint32_t idesc = make_idesc(T::kFormat, 256, 256, 0, 0);
-      const uint64_t d0 = make_smem_desc_sw128(smem_base);
-      constexpr uint64_t kStageInc = kFpStageBytes >> 4, kTileInc = kFpTileBytes >> 4, kKInc = 32u >> 4;
+      const uint32_t idesc = make_idesc(T::kFormat, 256, 256, NHWC ? 1 : 0, NHWC ? 1 : 0);
+      constexpr uint32_t kChanBlockBytes = (uint32_t)KB * kRowBytes;   // NHWC: one 128 B-wide channel block of a tile
+      const uint64_t d0 = !NHWC ? make_smem_desc_sw128(smem_base)
+                                : (KIND == KIND_TF32 ? make_smem_desc_sw128b32_mnmajor(smem_base, kChanBlockBytes)
+                                                     : make_smem_desc_sw128_mnmajor(smem_base, kChanBlockBytes));
+      // per MMA: K-major tiles advance 32 B inside the 128 B row, MN-major ones by UMMA_K position rows of 128 B
+      constexpr uint64_t kStageInc = kFpStageBytes >> 4, kTileInc = kFpTileBytes >> 4,
+                         kKInc = NHWC ? (T::kUmmaK * kRowBytes) >> 4 : 32u >> 4;
       const int full_kb = p.HW / KB;
       uint32_t stage = 0, phase = 0, it = 0;
       for (int u = pair; u < p.total_units; u += npairs, ++it) {

@@ -113,32 +113,36 @@ static int g_opt_bwd_pair = -1;
 static int g_opt_bwd_nt = 0;        // 0 = plan the x-tile width; 64..256 (multiple of 32) forces it (experiments)
 static int g_opt_tma_f32_type = 1;  // tensor-map data type for fp32 features: 0 = FLOAT32, 1 = TFLOAT32
 
-template <int KIND, int KP>
+template <int KIND, int KP, bool NHWC>
 static cudaError_t launch_gram_fwd_pair_one(const GramFwdParams& p, const CUtensorMap& map, int npairs, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(gram_fwd_pair_kernel<KIND, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(gram_fwd_pair_kernel<KIND, KP, NHWC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kFpSmemBytes);
   if (e != cudaSuccess) return e;
-  gram_fwd_pair_kernel<KIND, KP><<<2 * npairs, kFpThreads, kFpSmemBytes, st>>>(p, map);
+  gram_fwd_pair_kernel<KIND, KP, NHWC><<<2 * npairs, kFpThreads, kFpSmemBytes, st>>>(p, map);
   return cudaGetLastError();
 }
-template <int KIND>
+template <int KIND, bool NHWC>
 static cudaError_t launch_gram_fwd_pair(const GramFwdParams& p, const CUtensorMap& map, int kp, int npairs, cudaStream_t st) {
   switch (kp) {
-    case 0: return launch_gram_fwd_pair_one<KIND, 0>(p, map, npairs, st);
-    case 8: return launch_gram_fwd_pair_one<KIND, 8>(p, map, npairs, st);
-    case 16: return launch_gram_fwd_pair_one<KIND, 16>(p, map, npairs, st);
-    case 32: return launch_gram_fwd_pair_one<KIND, 32>(p, map, npairs, st);
-    case 64: return launch_gram_fwd_pair_one<KIND, 64>(p, map, npairs, st);
-    case 128: return launch_gram_fwd_pair_one<KIND, 128>(p, map, npairs, st);
+    case 0: return launch_gram_fwd_pair_one<KIND, 0, NHWC>(p, map, npairs, st);
+    case 8: return launch_gram_fwd_pair_one<KIND, 8, NHWC>(p, map, npairs, st);
+    case 16: return launch_gram_fwd_pair_one<KIND, 16, NHWC>(p, map, npairs, st);
+    case 32: return launch_gram_fwd_pair_one<KIND, 32, NHWC>(p, map, npairs, st);
+    case 64: return launch_gram_fwd_pair_one<KIND, 64, NHWC>(p, map, npairs, st);
+    case 128: return launch_gram_fwd_pair_one<KIND, 128, NHWC>(p, map, npairs, st);
     default: return cudaErrorInvalidValue;
   }
 }
 
-static int gram_fwd_common(const void* F, int f_dtype, long long img_stride, long long row_stride, int B, int C, int HW,
-                           int mode, int g, float* out, long long out_img_stride, int ksplit, int max_ctas,
-                           cudaStream_t st) {
+static int gram_fwd_common(const void* F, int f_dtype, long long img_stride, long long row_stride, long long x_stride,
+                           int B, int C, int HW, int mode, int g, float* out, long long out_img_stride, int ksplit,
+                           int max_ctas, cudaStream_t st) {
   if (!F || !out || B <= 0 || C <= 0 || HW <= 0) return GH_ERR_BAD_ARG;
   if (f_dtype != GH_DTYPE_F32 && f_dtype != GH_DTYPE_BF16) return GH_ERR_BAD_ARG;
+  // Layouts: x contiguous (NCHW: x_stride == 1, channel rows row_stride apart) or c contiguous (channels_last / NHWC:
+  // row_stride == 1, positions x_stride apart). The latter exists on the CTA-pair kernels only.
+  const bool nhwc = (x_stride != 1);
+  if (x_stride <= 0 || row_stride <= 0 || (nhwc && row_stride != 1)) return GH_ERR_BAD_ARG;
   int kp = 0;
   if (mode == GRAM_POOL) {
     if (g <= 0 || C % g != 0) return GH_ERR_UNSUPPORTED;
@@ -172,7 +176,11 @@ static int gram_fwd_common(const void* F, int f_dtype, long long img_stride, lon
   if (want_pair && sms >= 2) {
     CUtensorMap map;
     const int kb_elems = is_bf16 ? 64 : 32;
-    if (make_tensor_map_xcb(&map, F, is_bf16, img_stride, row_stride, B, C, HW, kb_elems, 128, g_opt_tma_f32_type)) {
+    const bool mapped = nhwc ? make_tensor_map_nhwc_mn(&map, F, is_bf16, img_stride, x_stride, B, C, HW, kb_elems, 128,
+                                                       g_opt_tma_f32_type)
+                             : make_tensor_map_xcb(&map, F, is_bf16, img_stride, row_stride, B, C, HW, kb_elems, 128,
+                                                   g_opt_tma_f32_type);
+    if (mapped) {
       GramFwdParams q = p;
       q.nkb = (HW + kb_elems - 1) / kb_elems;
       int npairs = ctas / 2;
@@ -191,12 +199,17 @@ static int gram_fwd_common(const void* F, int f_dtype, long long img_stride, lon
           if (e2 != cudaSuccess) return (int)e2;
         }
         if (tot < npairs) npairs = (int)tot;
-        e2 = is_bf16 ? launch_gram_fwd_pair<KIND_BF16>(q, map, kp, npairs, st)
-                     : launch_gram_fwd_pair<KIND_TF32>(q, map, kp, npairs, st);
+        if (nhwc)
+          e2 = is_bf16 ? launch_gram_fwd_pair<KIND_BF16, true>(q, map, kp, npairs, st)
+                       : launch_gram_fwd_pair<KIND_TF32, true>(q, map, kp, npairs, st);
+        else
+          e2 = is_bf16 ? launch_gram_fwd_pair<KIND_BF16, false>(q, map, kp, npairs, st)
+                       : launch_gram_fwd_pair<KIND_TF32, false>(q, map, kp, npairs, st);
         return (int)e2;
       }
     }
   }
+  if (nhwc) return GH_ERR_UNSUPPORTED;   // the ld.global kernels read NCHW rows only: the caller transposes (gh_transpose_cast)
   // every output element has exactly one writer unless K is split or a pooled row spans two epilogue warps (k > 32)
   p.use_atomics = (ksplit > 1 || kp > 32) ? 1 : 0;
 
@@ -223,11 +236,15 @@ static int gram_fwd_common(const void* F, int f_dtype, long long img_stride, lon
   return (int)e;
 }
 
-static int gram_bwd_common(const void* F, int f_dtype, long long img_stride, long long row_stride, int B, int C, int HW,
-                           int mode, int g, const float* dP, long long dp_img_stride, const float* dG, float* dF,
-                           long long df_img_stride, long long df_row_stride, int max_ctas, cudaStream_t st) {
+static int gram_bwd_common(const void* F, int f_dtype, long long img_stride, long long row_stride, long long x_stride,
+                           int B, int C, int HW, int mode, int g, const float* dP, long long dp_img_stride,
+                           const float* dG, float* dF, long long df_img_stride, long long df_row_stride,
+                           long long df_x_stride, int max_ctas, cudaStream_t st) {
   if (!F || !dF || B <= 0 || C <= 0 || HW <= 0) return GH_ERR_BAD_ARG;
   if (f_dtype != GH_DTYPE_F32 && f_dtype != GH_DTYPE_BF16) return GH_ERR_BAD_ARG;
+  const bool nhwc = (x_stride != 1);     // F and dF share the layout: both NCHW-like or both channels_last
+  if (x_stride <= 0 || row_stride <= 0 || df_x_stride <= 0 || df_row_stride <= 0) return GH_ERR_BAD_ARG;
+  if (nhwc != (df_x_stride != 1) || (nhwc && (row_stride != 1 || df_row_stride != 1))) return GH_ERR_BAD_ARG;
   if (C % 16 != 0) return GH_ERR_UNSUPPORTED;
   GramBwdParams p;
   p.F = F; p.img_stride = img_stride; p.row_stride = row_stride;
@@ -253,16 +270,24 @@ static int gram_bwd_common(const void* F, int f_dtype, long long img_stride, lon
     const bool want_pair = g_opt_bwd_pair != 0 && ctas_p >= 2 && (mode != GRAM_POOL || (g <= kBpMaxG && (C / g) >= 8));
     CUtensorMap tmF, tmD;
     const int kc_elems = is_bf16 ? 64 : 32;
-    if (want_pair &&
-        make_tensor_map_xcb(&tmF, F, is_bf16, img_stride, row_stride, B, C, HW, kc_elems, kc_elems, g_opt_tma_f32_type,
-                            /*atom32=*/!is_bf16) &&
-        make_tensor_map_xcb(&tmD, dF, false, df_img_stride, df_row_stride, B, C, HW, 32, 32, 0)) {
-      GramBwdPairParams q;
+    GramBwdPairParams q;
+    gbp_plan_tiles(HW, &q.NT, &q.nHT);
+    if (g_opt_bwd_nt) { q.NT = g_opt_bwd_nt; q.nHT = (HW + q.NT - 1) / q.NT; }
+    bool mapped = false;
+    if (want_pair) {
+      if (nhwc)     // F: K-major tiles [NT/2 position rows][128 B of channels]; dF: [32 x][32 c] tiles
+        mapped = make_tensor_map_nhwc_cxb(&tmF, F, is_bf16, img_stride, x_stride, B, C, HW, kc_elems, q.NT / 2,
+                                          g_opt_tma_f32_type) &&
+                 make_tensor_map_nhwc_cxb(&tmD, dF, false, df_img_stride, df_x_stride, B, C, HW, 32, 32, 0);
+      else
+        mapped = make_tensor_map_xcb(&tmF, F, is_bf16, img_stride, row_stride, B, C, HW, kc_elems, kc_elems,
+                                     g_opt_tma_f32_type, /*atom32=*/!is_bf16) &&
+                 make_tensor_map_xcb(&tmD, dF, false, df_img_stride, df_row_stride, B, C, HW, 32, 32, 0);
+    }
+    if (mapped) {
       q.B = B; q.C = C; q.HW = HW; q.mode = mode;
       q.dP = dP; q.dp_img_stride = dp_img_stride; q.g = g; q.kshift = p.kshift; q.dG = dG;
       q.scale = p.scale;
-      gbp_plan_tiles(HW, &q.NT, &q.nHT);
-      if (g_opt_bwd_nt) { q.NT = g_opt_bwd_nt; q.nHT = (HW + q.NT - 1) / q.NT; }
       q.nCB = (C + 255) / 256;
       q.nkc = (C + kc_elems - 1) / kc_elems;
       const long long tot = (long long)B * q.nHT * q.nCB;
@@ -271,23 +296,29 @@ static int gram_bwd_common(const void* F, int f_dtype, long long img_stride, lon
         int npairs = ctas_p / 2;
         if (tot < npairs) npairs = (int)tot;
         cudaError_t e3 = cudaErrorInvalidValue;
-#define GH_LAUNCH_BP(KIND, MODE)                                                                                       \
+#define GH_LAUNCH_BP(KIND, MODE, NHWC)                                                                                 \
         {                                                                                                              \
-          e3 = cudaFuncSetAttribute(gram_bwd_pair_kernel<KIND, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                    (int)kBpSmemBytes);                                                                \
+          e3 = cudaFuncSetAttribute(gram_bwd_pair_kernel<KIND, MODE, NHWC>,                                            \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBpSmemBytes);                   \
           if (e3 != cudaSuccess) return (int)e3;                                                                       \
-          gram_bwd_pair_kernel<KIND, MODE><<<2 * npairs, kBpThreads, kBpSmemBytes, st>>>(q, tmF, tmD);                 \
+          gram_bwd_pair_kernel<KIND, MODE, NHWC><<<2 * npairs, kBpThreads, kBpSmemBytes, st>>>(q, tmF, tmD);           \
+        }
+#define GH_LAUNCH_BP2(KIND, MODE)                                                                                      \
+        {                                                                                                              \
+          if (nhwc) GH_LAUNCH_BP(KIND, MODE, true) else GH_LAUNCH_BP(KIND, MODE, false)                                \
         }
         if (is_bf16) {
-          if (mode == GRAM_POOL) GH_LAUNCH_BP(KIND_BF16, GRAM_POOL) else GH_LAUNCH_BP(KIND_BF16, GRAM_DENSE)
+          if (mode == GRAM_POOL) GH_LAUNCH_BP2(KIND_BF16, GRAM_POOL) else GH_LAUNCH_BP2(KIND_BF16, GRAM_DENSE)
         } else {
-          if (mode == GRAM_POOL) GH_LAUNCH_BP(KIND_TF32, GRAM_POOL) else GH_LAUNCH_BP(KIND_TF32, GRAM_DENSE)
+          if (mode == GRAM_POOL) GH_LAUNCH_BP2(KIND_TF32, GRAM_POOL) else GH_LAUNCH_BP2(KIND_TF32, GRAM_DENSE)
         }
+#undef GH_LAUNCH_BP2
 #undef GH_LAUNCH_BP
         return (int)cudaGetLastError();
       }
     }
   }
+  if (nhwc) return GH_ERR_UNSUPPORTED;   // the ld.global kernels read / write NCHW rows only: the caller transposes
   if (g_opt_bwd_variant == 2) {
     GramBwd2Params q;
     q.F = F; q.img_stride = img_stride; q.row_stride = row_stride;
@@ -485,16 +516,16 @@ int gh_last_device_error(unsigned int* out4) {
   return (int)e;
 }
 
-int gh_gram_pool_fwd(const void* F, int f_dtype, long long img_stride, long long row_stride, int B, int C, int HW,
-                     int g, float* desc, int l, int L, int ksplit, int max_ctas, void* stream) {
+int gh_gram_pool_fwd(const void* F, int f_dtype, long long img_stride, long long row_stride, long long x_stride, int B,
+                     int C, int HW, int g, float* desc, int l, int L, int ksplit, int max_ctas, void* stream) {
   if (!desc || l < 0 || l >= L || g <= 0) return GH_ERR_BAD_ARG;
-  return gram_fwd_common(F, f_dtype, img_stride, row_stride, B, C, HW, GRAM_POOL, g, desc + (long long)l * g * g,
+  return gram_fwd_common(F, f_dtype, img_stride, row_stride, x_stride, B, C, HW, GRAM_POOL, g, desc + (long long)l * g * g,
                          (long long)L * g * g, ksplit, max_ctas, (cudaStream_t)stream);
 }
 
-int gh_gram_dense_fwd(const void* F, int f_dtype, long long img_stride, long long row_stride, int B, int C, int HW,
-                      float* G, int ksplit, int max_ctas, void* stream) {
-  return gram_fwd_common(F, f_dtype, img_stride, row_stride, B, C, HW, GRAM_DENSE, 0, G, (long long)C * C, ksplit,
+int gh_gram_dense_fwd(const void* F, int f_dtype, long long img_stride, long long row_stride, long long x_stride, int B,
+                      int C, int HW, float* G, int ksplit, int max_ctas, void* stream) {
+  return gram_fwd_common(F, f_dtype, img_stride, row_stride, x_stride, B, C, HW, GRAM_DENSE, 0, G, (long long)C * C, ksplit,
                          max_ctas, (cudaStream_t)stream);
 }
 
@@ -515,20 +546,20 @@ int gh_adaptive_pool_bwd(const float* d_desc, int l, int L, int B, int C, int g,
   return (int)cudaGetLastError();
 }
 
-int gh_gram_pool_bwd(const void* F, int f_dtype, long long img_stride, long long row_stride, int B, int C, int HW,
-                     int g, const float* d_desc, int l, int L, float* dF, long long df_img_stride,
-                     long long df_row_stride, int max_ctas, void* stream) {
+int gh_gram_pool_bwd(const void* F, int f_dtype, long long img_stride, long long row_stride, long long x_stride, int B,
+                     int C, int HW, int g, const float* d_desc, int l, int L, float* dF, long long df_img_stride,
+                     long long df_row_stride, long long df_x_stride, int max_ctas, void* stream) {
   if (!d_desc || l < 0 || l >= L || g <= 0) return GH_ERR_BAD_ARG;
-  return gram_bwd_common(F, f_dtype, img_stride, row_stride, B, C, HW, GRAM_POOL, g, d_desc + (long long)l * g * g,
-                         (long long)L * g * g, nullptr, dF, df_img_stride, df_row_stride, max_ctas,
-                         (cudaStream_t)stream);
+  return gram_bwd_common(F, f_dtype, img_stride, row_stride, x_stride, B, C, HW, GRAM_POOL, g,
+                         d_desc + (long long)l * g * g, (long long)L * g * g, nullptr, dF, df_img_stride, df_row_stride,
+                         df_x_stride, max_ctas, (cudaStream_t)stream);
 }
 
-int gh_gram_dense_bwd(const void* F, int f_dtype, long long img_stride, long long row_stride, int B, int C, int HW,
-                      const float* dG, float* dF, long long df_img_stride, long long df_row_stride, int max_ctas,
-                      void* stream) {
-  return gram_bwd_common(F, f_dtype, img_stride, row_stride, B, C, HW, GRAM_DENSE, 0, nullptr, 0, dG, dF,
-                         df_img_stride, df_row_stride, max_ctas, (cudaStream_t)stream);
+int gh_gram_dense_bwd(const void* F, int f_dtype, long long img_stride, long long row_stride, long long x_stride, int B,
+                      int C, int HW, const float* dG, float* dF, long long df_img_stride, long long df_row_stride,
+                      long long df_x_stride, int max_ctas, void* stream) {
+  return gram_bwd_common(F, f_dtype, img_stride, row_stride, x_stride, B, C, HW, GRAM_DENSE, 0, nullptr, 0, dG, dF,
+                         df_img_stride, df_row_stride, df_x_stride, max_ctas, (cudaStream_t)stream);
 }
 
 int gh_attn_head_fwd(const float* desc, const float* W_in, const float* b_in, const float* W_out, const float* b_out,

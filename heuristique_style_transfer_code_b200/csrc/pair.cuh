@@ -157,6 +157,13 @@ __device__ __forceinline__ void tma_load_3d_pair(uint32_t dst_smem, const CUtens
       ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst_smem, const CUtensorMap* tmap, uint32_t bar_cluster,
+                                                 int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 // Tile store shared -> global (clipped at the tensor bounds), tracked by the issuing thread's bulk async-group.
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tmap, uint32_t src_smem, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
@@ -223,6 +230,52 @@ inline bool make_tensor_map_xcb(CUtensorMap* map, const void* base, bool is_bf16
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// ---- channels-last (NHWC) features: element (b, c, x) at base[b*img_stride + x*x_stride + c], c contiguous ----------
+// Operand tiles whose MN index is the channel (the Gram forward): 128 B rows run along c, so the canonical MN-major tile
+// of R channels x K positions is R/E atoms of [K positions][E channels] (E = 128 B of elements). One 4-D box fetches
+// all atoms of a tile: dims (c within atom, x, atom, b), box E x box_x x (R/E) x 1, landing as [atom][x][E].
+// tf32 MN-major operands need the 32 B-atom flavour of the 128 B swizzle.
+inline bool make_tensor_map_nhwc_mn(CUtensorMap* map, const void* base, bool is_bf16, long long img_stride,
+                                    long long x_stride, int B, int C, int HW, int box_x, int rows, int f32_type) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return false;
+  const long long es = is_bf16 ? 2 : 4;
+  const int E = (int)(128 / es);
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) || (x_stride * es) % 16 || (img_stride * es) % 16) return false;
+  if (C % E != 0 || rows % E != 0 || x_stride < C || img_stride <= 0 || box_x < 1 || box_x > 256) return false;
+  if (x_stride * es >= (1LL << 40) || img_stride * es >= (1LL << 40)) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)E, (cuuint64_t)HW, (cuuint64_t)(C / E), (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)(x_stride * es), (cuuint64_t)128, (cuuint64_t)(img_stride * es)};
+  cuuint32_t box[4] = {(cuuint32_t)E, (cuuint32_t)box_x, (cuuint32_t)(rows / E), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUtensorMapDataType dt = is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                 : (f32_type == 1 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+  CUresult r = enc(map, dt, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   is_bf16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+// The same tensor as a 3-D map (c, x, b) with a box of box_c x box_x x 1 and the plain 128 B swizzle: K-major operand
+// tiles whose K index is the channel (the backward's F operand: [x rows][128 B of channels]) and the NHWC gradient store.
+inline bool make_tensor_map_nhwc_cxb(CUtensorMap* map, const void* base, bool is_bf16, long long img_stride,
+                                     long long x_stride, int B, int C, int HW, int box_c, int box_x, int f32_type) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return false;
+  const long long es = is_bf16 ? 2 : 4;
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) || (x_stride * es) % 16 || (img_stride * es) % 16) return false;
+  if (x_stride < C || img_stride <= 0 || box_c * es != 128 || box_x < 1 || box_x > 256) return false;
+  if (x_stride * es >= (1LL << 40) || img_stride * es >= (1LL << 40)) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)HW, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)(x_stride * es), (cuuint64_t)(img_stride * es)};
+  cuuint32_t box[3] = {(cuuint32_t)box_c, (cuuint32_t)box_x, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapDataType dt = is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                 : (f32_type == 1 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+  CUresult r = enc(map, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 

@@ -51,13 +51,16 @@ def _require_cuda(t: torch.Tensor, what: str) -> None:
         raise GramHeadError(f"gramhead: {what} must be a CUDA tensor (got {t.device}); the head has no CPU path")
 
 
-def _feature_view(x: torch.Tensor) -> Tuple[torch.Tensor, int, int, int, int, int, int]:
-    """(B, C, H, W) or (B, C, HW) activation -> tensor kept alive, dtype code, img/row strides (elements), B, C, HW."""
+def _feature_view(x: torch.Tensor):
+    """(B, C, H, W) or (B, C, HW) activation -> (tensor kept alive, dtype code, img / channel / position strides in
+    elements, B, C, HW). Dense channels_last (NHWC) 4-D tensors are passed through with channel stride 1; anything
+    else is brought to x-contiguous rows (what the reference's .view(b, ch, h*w) requires)."""
     _require_cuda(x, "features")
     if x.dim() == 4:
         b, c, h, w = x.shape
         hw = h * w
-        # NCHW-contiguous spatial dims are required (the reference does .view(b, ch, h*w)); batch/channel may stride
+        if is_channels_last(x):
+            return x, _dtype_code(x), x.stride(0), 1, c, b, c, hw
         if not (x.stride(3) == 1 and x.stride(2) == w):
             x = x.contiguous()
     elif x.dim() == 3:
@@ -66,13 +69,7 @@ def _feature_view(x: torch.Tensor) -> Tuple[torch.Tensor, int, int, int, int, in
             x = x.contiguous()
     else:
         raise GramHeadError(f"gramhead: features must be (B,C,H,W) or (B,C,HW), got {tuple(x.shape)}")
-    if x.dtype == torch.float32:
-        code = GH_DTYPE_F32
-    elif x.dtype == torch.bfloat16:
-        code = GH_DTYPE_BF16
-    else:
-        raise GramHeadError(f"gramhead: features must be float32 or bfloat16, got {x.dtype}")
-    return x, code, x.stride(0), x.stride(1), b, c, hw
+    return x, _dtype_code(x), x.stride(0), x.stride(1), 1, b, c, hw
 
 
 def _dtype_code(t: torch.Tensor) -> int:
@@ -125,6 +122,26 @@ def grad_like_activation(df: torch.Tensor, shape, dtype, channels_last: bool) ->
     return out
 
 
+def _layout_tag(s_x: int) -> str:
+    return "" if s_x == 1 else ",nhwc"
+
+
+def nhwc_native(x: torch.Tensor, g: int = 0) -> bool:
+    """True when a channels_last activation can be consumed as it is by the CTA-pair kernels (forward AND backward):
+    channels a multiple of one 128 B row, 16 B-aligned storage and, for the pooled path, the shapes the generated
+    backward handles (k = C/g a power of two >= 8, g <= 32). Otherwise it goes through nhwc_to_nchw()."""
+    if not is_channels_last(x):
+        return False
+    c = x.shape[1]
+    per_row = 128 // x.element_size()
+    if c % per_row or x.data_ptr() % 16 or x.dtype not in (torch.float32, torch.bfloat16):
+        return False
+    if g:
+        k = c // g if c % g == 0 else 0
+        return g <= 32 and k >= 8 and (k & (k - 1)) == 0 and k <= 128
+    return True
+
+
 def pooled_supported(c: int, g: int) -> bool:
     """True when the fused Gram+pool kernels apply (bins are disjoint k x k blocks, k a power of two in [8, 128])."""
     if g <= 0 or c % g:
@@ -138,46 +155,55 @@ def pooled_supported(c: int, g: int) -> bool:
 # ----------------------------------------------------------------------------------------------------------------------
 def gram_pool_fwd_(x: torch.Tensor, g: int, desc: torch.Tensor, l: int) -> None:
     """desc[:, l, :] = vec(pool_g(F F^T / HW)) for stage activation x. desc: (B, L, g*g) fp32 contiguous."""
-    x, code, s_img, s_row, b, c, hw = _feature_view(x)
+    x, code, s_img, s_row, s_x, b, c, hw = _feature_view(x)
     assert desc.is_contiguous() and desc.dtype == torch.float32 and desc.shape[0] == b and desc.shape[2] == g * g
     work = dict(bytes=b * c * hw * x.element_size() + b * g * g * 4, flops=b * c * (c + 1) * hw, kind="gram_fwd")
-    with torch.cuda.device(x.device), _Timed(f"gram_pool_fwd[C={c},HW={hw},{x.dtype}]", 1, x.device, **work):
-        rc = _lib.lib().gh_gram_pool_fwd(x.data_ptr(), code, s_img, s_row, b, c, hw, g, desc.data_ptr(), l,
+    with torch.cuda.device(x.device), _Timed(f"gram_pool_fwd[C={c},HW={hw},{x.dtype}{_layout_tag(s_x)}]", 1, x.device, **work):
+        rc = _lib.lib().gh_gram_pool_fwd(x.data_ptr(), code, s_img, s_row, s_x, b, c, hw, g, desc.data_ptr(), l,
                                          desc.shape[1], KSPLIT, MAX_CTAS, _stream_ptr(x))
     check(rc, "gh_gram_pool_fwd")
 
 
 def gram_dense_fwd(x: torch.Tensor) -> torch.Tensor:
-    x, code, s_img, s_row, b, c, hw = _feature_view(x)
+    x, code, s_img, s_row, s_x, b, c, hw = _feature_view(x)
     out = torch.empty((b, c, c), device=x.device, dtype=torch.float32)
     work = dict(bytes=b * c * hw * x.element_size() + b * c * c * 4, flops=b * c * (c + 1) * hw, kind="gram_fwd")
-    with torch.cuda.device(x.device), _Timed(f"gram_dense_fwd[C={c},HW={hw},{x.dtype}]", 1, x.device, **work):
-        rc = _lib.lib().gh_gram_dense_fwd(x.data_ptr(), code, s_img, s_row, b, c, hw, out.data_ptr(), KSPLIT, MAX_CTAS,
-                                          _stream_ptr(x))
+    with torch.cuda.device(x.device), _Timed(f"gram_dense_fwd[C={c},HW={hw},{x.dtype}{_layout_tag(s_x)}]", 1, x.device, **work):
+        rc = _lib.lib().gh_gram_dense_fwd(x.data_ptr(), code, s_img, s_row, s_x, b, c, hw, out.data_ptr(), KSPLIT,
+                                          MAX_CTAS, _stream_ptr(x))
     check(rc, "gh_gram_dense_fwd")
     return out
 
 
+def _grad_buffer(x: torch.Tensor, s_x: int, b: int, c: int, hw: int):
+    """fp32 dF in the layout of the features: (B, C, HW) rows, or channels_last like x. -> (tensor, img, row, x strides)"""
+    if s_x == 1:
+        return torch.empty((b, c, hw), device=x.device, dtype=torch.float32), c * hw, hw, 1
+    df = torch.empty(x.shape, device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
+    return df, c * hw, 1, c
+
+
 def gram_pool_bwd(x: torch.Tensor, g: int, d_desc: torch.Tensor, l: int) -> torch.Tensor:
-    x, code, s_img, s_row, b, c, hw = _feature_view(x)
+    """-> fp32 dF, (B, C, HW) for x-contiguous features, channels_last (B, C, H, W) for channels_last features."""
+    x, code, s_img, s_row, s_x, b, c, hw = _feature_view(x)
     d_desc = d_desc.contiguous()
-    df = torch.empty((b, c, hw), device=x.device, dtype=torch.float32)
+    df, d_img, d_row, d_x = _grad_buffer(x, s_x, b, c, hw)
     work = dict(bytes=b * c * hw * (x.element_size() + 4) + b * g * g * 4, flops=2 * b * c * c * hw, kind="gram_bwd")
-    with torch.cuda.device(x.device), _Timed(f"gram_pool_bwd[C={c},HW={hw},{x.dtype}]", 1, x.device, **work):
-        rc = _lib.lib().gh_gram_pool_bwd(x.data_ptr(), code, s_img, s_row, b, c, hw, g, d_desc.data_ptr(), l,
-                                         d_desc.shape[1], df.data_ptr(), c * hw, hw, MAX_CTAS, _stream_ptr(x))
+    with torch.cuda.device(x.device), _Timed(f"gram_pool_bwd[C={c},HW={hw},{x.dtype}{_layout_tag(s_x)}]", 1, x.device, **work):
+        rc = _lib.lib().gh_gram_pool_bwd(x.data_ptr(), code, s_img, s_row, s_x, b, c, hw, g, d_desc.data_ptr(), l,
+                                         d_desc.shape[1], df.data_ptr(), d_img, d_row, d_x, MAX_CTAS, _stream_ptr(x))
     check(rc, "gh_gram_pool_bwd")
     return df
 
 
 def gram_dense_bwd(x: torch.Tensor, d_gram: torch.Tensor) -> torch.Tensor:
-    x, code, s_img, s_row, b, c, hw = _feature_view(x)
+    x, code, s_img, s_row, s_x, b, c, hw = _feature_view(x)
     d_gram = d_gram.contiguous().float()
-    df = torch.empty((b, c, hw), device=x.device, dtype=torch.float32)
+    df, d_img, d_row, d_x = _grad_buffer(x, s_x, b, c, hw)
     work = dict(bytes=b * c * hw * (x.element_size() + 4) + b * c * c * 4, flops=2 * b * c * c * hw, kind="gram_bwd")
-    with torch.cuda.device(x.device), _Timed(f"gram_dense_bwd[C={c},HW={hw},{x.dtype}]", 1, x.device, **work):
-        rc = _lib.lib().gh_gram_dense_bwd(x.data_ptr(), code, s_img, s_row, b, c, hw, d_gram.data_ptr(), df.data_ptr(),
-                                          c * hw, hw, MAX_CTAS, _stream_ptr(x))
+    with torch.cuda.device(x.device), _Timed(f"gram_dense_bwd[C={c},HW={hw},{x.dtype}{_layout_tag(s_x)}]", 1, x.device, **work):
+        rc = _lib.lib().gh_gram_dense_bwd(x.data_ptr(), code, s_img, s_row, s_x, b, c, hw, d_gram.data_ptr(),
+                                          df.data_ptr(), d_img, d_row, d_x, MAX_CTAS, _stream_ptr(x))
     check(rc, "gh_gram_dense_bwd")
     return df
 
@@ -224,7 +250,7 @@ class _GramDense(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x):
-        ctx.meta = (tuple(x.shape), x.dtype, is_channels_last(x))
+        ctx.meta = (tuple(x.shape), x.dtype, is_channels_last(x) and not nhwc_native(x))
         if ctx.meta[2]:
             x = nhwc_to_nchw(x)
         ctx.save_for_backward(x)
@@ -234,6 +260,8 @@ class _GramDense(torch.autograd.Function):
     def backward(ctx, d_gram):
         (x,) = ctx.saved_tensors
         df = gram_dense_bwd(x, d_gram)
+        if df.dim() == 4:                       # channels_last features consumed natively: dF is already NHWC
+            return df.to(ctx.meta[1])
         return grad_like_activation(df, *ctx.meta)
 
 
@@ -249,9 +277,10 @@ class _StyleDescriptor(torch.autograd.Function):
         b = stages[0].shape[0]
         L = len(stages)
         desc = torch.empty((b, L, g * g), device=stages[0].device, dtype=torch.float32)
-        ctx.meta = [(tuple(x.shape), x.dtype, is_channels_last(x)) for x in stages]
-        # channels_last (NHWC) activations: one transpose pass gives the C x HW matrices the Gram kernels consume; the
-        # NCHW copy is what backward re-reads, so it is the tensor saved (the backbone keeps the original alive anyway)
+        # channels_last (NHWC) activations are consumed as they are by the CTA-pair kernels (MN-major operand tiles) when
+        # nhwc_native() holds; otherwise one transpose pass gives the C x HW matrices the other kernels need, and that
+        # NCHW copy is the tensor saved for backward (the backbone keeps the original alive anyway)
+        ctx.meta = [(tuple(x.shape), x.dtype, is_channels_last(x) and not nhwc_native(x, g)) for x in stages]
         stages = [nhwc_to_nchw(x) if m[2] else x for x, m in zip(stages, ctx.meta)]
         for l, x in enumerate(stages):
             if pooled_supported(x.shape[1], g):
@@ -276,7 +305,10 @@ class _StyleDescriptor(torch.autograd.Function):
                 df = gram_pool_bwd(x, g, d_desc, l)
             else:
                 df = gram_dense_bwd(x, adaptive_pool_bwd(d_desc, l, c, g))
-            grads.append(grad_like_activation(df, *ctx.meta[l]))
+            if df.dim() == 4:                   # channels_last features consumed natively: dF is already NHWC
+                grads.append(df.to(ctx.meta[l][1]))
+            else:
+                grads.append(grad_like_activation(df, *ctx.meta[l]))
         return tuple(grads)
 
 

@@ -48,20 +48,23 @@ int gh_last_device_error(unsigned int* out4);
  *   gram_matrix():            Models/Models_RESNET50_TRUNCATE_GRAM_with_Attention.py:26-30 (bmm + div(h*w))
  *   adaptive_avg_pool2d:      :51-52
  *   stack/flatten (layout):   :54-55
- * F: (B, C, HW) features, element (b,c,x) at F[b*img_stride + c*row_stride + x], dtype f_dtype.
+ * F: (B, C, HW) features, element (b,c,x) at F[b*img_stride + c*row_stride + x*x_stride], dtype f_dtype. Two layouts:
+ *   x contiguous (NCHW as cuDNN's default leaves it):  x_stride == 1, row_stride >= HW;
+ *   c contiguous (channels_last / NHWC):               row_stride == 1, x_stride >= C  (CTA-pair kernels only:
+ *   GH_ERR_UNSUPPORTED when TMA cannot describe the tensor -- transpose with gh_transpose_cast instead).
  * desc: (B, L, g*g) fp32; this call overwrites desc[:, l, :] with vec_rowmajor(pool_g(F F^T / HW)).
  * Requires C % g == 0 and k = C/g a power of two in [8, 128] (returns GH_ERR_UNSUPPORTED otherwise: use
  * gh_gram_dense_fwd + gh_adaptive_pool_fwd, which implement torch's general bin rule).
  * ksplit: number of K (=HW) partitions per tile whose partial sums meet in fp32 atomics; 0 = choose for load balance,
  * 1 = deterministic summation order. max_ctas: 0 = one persistent CTA per SM. */
-int gh_gram_pool_fwd(const void* F, int f_dtype, long long img_stride, long long row_stride, int B, int C, int HW,
-                     int g, float* desc, int l, int L, int ksplit, int max_ctas, void* stream);
+int gh_gram_pool_fwd(const void* F, int f_dtype, long long img_stride, long long row_stride, long long x_stride, int B,
+                     int C, int HW, int g, float* desc, int l, int L, int ksplit, int max_ctas, void* stream);
 
 /* Dense Gram, forward: G[b] = F[b] F[b]^T / HW, (B, C, C) fp32, both triangles written.
  * Replaces gram_matrix() used on its own (:26-30; style-transfer mode,
  * functions/functions_RESNET50_Truncate_Gram_Attention.py:273-275,290-291). */
-int gh_gram_dense_fwd(const void* F, int f_dtype, long long img_stride, long long row_stride, int B, int C, int HW,
-                      float* G, int ksplit, int max_ctas, void* stream);
+int gh_gram_dense_fwd(const void* F, int f_dtype, long long img_stride, long long row_stride, long long x_stride, int B,
+                      int C, int HW, float* G, int ksplit, int max_ctas, void* stream);
 
 /* torch.nn.functional.adaptive_avg_pool2d(G, (g, g)) on (B, C, C) with torch's bin rule
  * [floor(i*C/g), ceil((i+1)*C/g)), written to desc[:, l, :] of a (B, L, g*g) buffer.  (:51-55) */
@@ -71,16 +74,17 @@ int gh_adaptive_pool_bwd(const float* d_desc, int l, int L, int B, int C, int g,
 
 /* Pooled Gram, backward (autograd of the three reference lines above):
  *   dF[b] = (dG + dG^T) F[b] / HW,  dG[c][d] = d_desc[b, l, (c/k)*g + d/k] / k^2.
- * dF: fp32, element (b,c,x) at dF[b*df_img_stride + c*df_row_stride + x]; overwritten.
+ * dF: fp32, element (b,c,x) at dF[b*df_img_stride + c*df_row_stride + x*df_x_stride]; overwritten. F and dF must use
+ * the same layout (both x contiguous or both c contiguous, see gh_gram_pool_fwd).
  * Requires C % g == 0, k a power of two, g <= 64, C % 16 == 0. */
-int gh_gram_pool_bwd(const void* F, int f_dtype, long long img_stride, long long row_stride, int B, int C, int HW,
-                     int g, const float* d_desc, int l, int L, float* dF, long long df_img_stride,
-                     long long df_row_stride, int max_ctas, void* stream);
+int gh_gram_pool_bwd(const void* F, int f_dtype, long long img_stride, long long row_stride, long long x_stride, int B,
+                     int C, int HW, int g, const float* d_desc, int l, int L, float* dF, long long df_img_stride,
+                     long long df_row_stride, long long df_x_stride, int max_ctas, void* stream);
 
 /* Dense Gram, backward: dF[b] = (dG[b] + dG[b]^T) F[b] / HW with dG (B, C, C) fp32. Requires C % 16 == 0. */
-int gh_gram_dense_bwd(const void* F, int f_dtype, long long img_stride, long long row_stride, int B, int C, int HW,
-                      const float* dG, float* dF, long long df_img_stride, long long df_row_stride, int max_ctas,
-                      void* stream);
+int gh_gram_dense_bwd(const void* F, int f_dtype, long long img_stride, long long row_stride, long long x_stride, int B,
+                      int C, int HW, const float* dG, float* dF, long long df_img_stride, long long df_row_stride,
+                      long long df_x_stride, int max_ctas, void* stream);
 
 /* Attention over the L stage descriptors + mean over stages + classifier, forward.  Replaces
  *   permute + self.attention(X, X, X) (nn.MultiheadAttention, 1 head): :56-58

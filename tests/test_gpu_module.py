@@ -152,7 +152,7 @@ def test_transpose_cast_kernel_is_exact(B, R, S):
             assert bool((out[:, :, R:] == -7.0).all())                      # the padding is not written
 
 
-def test_channels_last_activations_take_the_transpose_path_and_match_nchw():
+def test_channels_last_activations_match_nchw():
     import torch
     from heuristique_style_transfer_code_b200 import ops
     torch.manual_seed(0)
@@ -173,11 +173,13 @@ def test_channels_last_activations_take_the_transpose_path_and_match_nchw():
         finally:
             ops.KSPLIT = 0
         torch.cuda.synchronize()
-        assert torch.equal(da, db)                                   # same C x HW matrices reach the same kernels
+        # fp32 / C % 32 == 0 and bf16 / C % 64 == 0 are consumed as NHWC (MN-major tiles), the rest is transposed first:
+        # same operands, same K order -> equal up to fp32 summation order inside the tensor core
+        assert float((da - db).norm() / da.norm()) <= 1e-6
         for ta, tb in zip(a, b):
             assert ops.is_channels_last(tb.grad) and tb.grad.dtype == dtype
-            assert torch.equal(ta.grad, tb.grad.contiguous())
-        assert torch.equal(Ga, Gb)
+            assert float((ta.grad.float() - tb.grad.float()).norm() / ta.grad.float().norm()) <= (1e-5 if dtype == torch.float32 else 1e-2)
+        assert float((Ga - Gb).norm() / Ga.norm()) <= 1e-6
 
 
 def test_backbone_modes_agree_with_the_reference_mode():

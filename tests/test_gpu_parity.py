@@ -345,3 +345,61 @@ def _full_size_properties(ops, C, HW, path):
     xs = x[:16]
     ref = torch.nn.functional.adaptive_avg_pool2d(torch.bmm(xs, xs.transpose(1, 2)).div(HW), (g, g)).flatten(1)
     assert float((base[:16, 0] - ref).norm() / ref.norm()) <= 1e-3
+
+
+# ---- channels_last (NHWC) features consumed natively by the CTA-pair kernels (MN-major operand tiles) -----------------
+@pytest.mark.parametrize("B,C,H,W,g,dtype", [(2, 256, 56, 56, 32, "f32"), (3, 512, 28, 28, 32, "f32"), (2, 1024, 14, 14, 32, "f32"),
+                                             (2, 256, 56, 56, 32, "bf16"), (3, 512, 28, 28, 32, "bf16"), (2, 1024, 14, 14, 32, "bf16"),
+                                             (2, 384, 10, 20, 48, "f32"), (5, 256, 112, 112, 32, "f32"), (2, 64, 10, 10, 8, "f32")])
+def test_channels_last_features_forward_backward(ops, B, C, H, W, g, dtype):
+    torch.manual_seed(0)
+    x = torch.relu(torch.randn(B, C, H, W, device="cuda"))
+    if dtype == "bf16":
+        x = x.bfloat16()
+    xcl = x.contiguous(memory_format=torch.channels_last)
+    native = ops.nhwc_native(xcl, g)
+    assert native == (C % (32 if dtype == "f32" else 64) == 0 and g <= 32)
+    desc = torch.full((B, 2, g * g), float("nan"), device="cuda")
+    ops.KSPLIT = 1
+    try:
+        a = xcl.clone().requires_grad_(True)
+        d = ops.style_descriptor([a], g)
+        w = torch.randn_like(d)
+        (d * w).sum().backward()
+        if native:
+            ops.gram_pool_fwd_(xcl, g, desc, 1)          # the raw entry point on the NHWC tensor
+    finally:
+        ops.KSPLIT = 0
+    torch.cuda.synchronize()
+    xf = npf(x).reshape(B, C, H * W)
+    ref = O.descriptors([xf], g)[:, 0]
+    assert O.rel_err(npf(d[:, 0]), ref) <= 1e-3
+    # one fp32 accumulator over all HW positions (KSPLIT = 1): summation-order error grows with K (12 544 at 112 x 112)
+    assert operand_model_err(npf(d[:, 0]), lambda f: O.descriptors([f], g)[:, 0], xf, "pair", dtype) <= (1e-5 if H * W <= 4096 else 1e-4)
+    if native:
+        assert torch.isnan(desc[:, 0]).all() and torch.equal(desc[:, 1], d[:, 0])
+    gref = O.gram_pool_backward(xf, g, npf(w[:, 0])).reshape(B, C, H, W)
+    assert a.grad.dtype == x.dtype and ops.is_channels_last(a.grad)
+    err = O.rel_err(npf(a.grad), gref)
+    assert err <= (1e-3 if dtype == "f32" and g <= 32 else 6e-3)
+
+
+@pytest.mark.parametrize("B,C,H,W", [(1, 64, 56, 56), (2, 256, 14, 14), (1, 512, 10, 10)])
+def test_channels_last_dense_gram(ops, B, C, H, W):
+    torch.manual_seed(0)
+    x = torch.relu(torch.randn(B, C, H, W, device="cuda")).contiguous(memory_format=torch.channels_last)
+    a = x.clone().requires_grad_(True)
+    ops.KSPLIT = 1
+    try:
+        G = ops.gram_matrix(a)
+        dg = torch.randn_like(G)
+        (G * dg).sum().backward()
+    finally:
+        ops.KSPLIT = 0
+    torch.cuda.synchronize()
+    xf = npf(x).reshape(B, C, H * W)
+    assert O.rel_err(npf(G), O.gram(xf)) <= 1e-3
+    assert operand_model_err(npf(G), O.gram, xf, "pair", "f32") <= 1e-5
+    assert float((G - G.transpose(1, 2)).abs().max()) <= 1e-6 * float(G.abs().max())
+    assert ops.is_channels_last(a.grad)
+    assert O.rel_err(npf(a.grad), O.gram_dense_backward(xf, npf(dg)).reshape(B, C, H, W)) <= 1e-3
