@@ -138,7 +138,11 @@ def summarise_profile(records, peaks):
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.isfile(tpath):
-        traffic = json.load(open(tpath)).get(top)
+        table = json.load(open(tpath))
+        traffic = table.get(top)
+        captured = table.get("_algorithmic_bytes_of_captured_launch", {}).get(top)
+        if traffic is not None and captured:          # ncu capture was taken at batch 256: scale to this launch's size
+            traffic = int(round(traffic * a["work"]["bytes"] / captured))
     roof = dict(kernel=top, bound=bound, achieved=round(ach, 1), peak=peak, unit=unit, frac=round(ach / peak, 4),
                 traffic=traffic, avg_launch_us=round(ms * 1e3, 2), algorithmic_bytes=a["work"]["bytes"],
                 algorithmic_flops=a["work"]["flops"], peak_source=peaks["source"],
@@ -184,7 +188,7 @@ def run_reference(args):
                                        "reference's op sequence; /root/reference is not on this box)"},
             "e2e": {"value": round(ips, 2), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 def run_ours(args):
@@ -368,10 +372,31 @@ def run_ours(args):
                           "head_images_per_s": round(B / (head_ms / 1e3), 1), "kernels": kernels},
             "backbone_handoff": handoff,
             "train": train}
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
+
+
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """Keep stdout for the one JSON line: libraries that write to fd 1 (NCCL prints its version there) go to stderr."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(text):
+    sys.stdout.flush()
+    if _RESULT_FD is None:
+        print(text, flush=True)
+    else:
+        os.write(_RESULT_FD, (text + "\n").encode())
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -19,6 +19,29 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_cpus(device: torch.device) -> Optional[Sequence[int]]:
+    """Pins this process to the CPU cores NVML reports as local to `device` (same NUMA node / PCIe root), so the pinned
+    staging buffers it allocates afterwards and its launch thread sit next to the GPU. With several ranks on a
+    two-socket box the scheduler otherwise places ranks on the remote socket and host->device copies cross the
+    inter-socket link. A placement hint only: returns None (and changes nothing) when NVML cannot answer."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        p = torch.cuda.get_device_properties(device)
+        bus_id = f"{p.pci_domain_id:08x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus_id.encode())
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
+
+
 def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int, torch.device]:
     """Reads RANK / WORLD_SIZE / LOCAL_RANK / MASTER_* (torchrun). Single-process when WORLD_SIZE is absent or 1."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -28,6 +51,9 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int, torch.d
     device = torch.device(f"cuda:{local}") if use_cuda else torch.device("cpu")
     if use_cuda:
         torch.cuda.set_device(device)
+        want = os.environ.get("GRAMHEAD_CPU_AFFINITY", "auto")
+        if want == "1" or (want == "auto" and world > 1):
+            bind_to_gpu_cpus(device)
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")

@@ -1,5 +1,5 @@
 """Tiny single-kernel drivers for `ncu --set full` captures (a few launches, nothing else on the GPU).
-    python tools/prof_one.py bwd|fwd|gemm [C HW B [f32|bf16 [pair(-1|0|1)]]]"""
+    python tools/prof_one.py bwd|fwd|gemm [C HW B [f32|bf16 [pair(-1|0|1) [nchw|nhwc]]]]"""
 import os
 import sys
 
@@ -12,6 +12,7 @@ kind = sys.argv[1] if len(sys.argv) > 1 else "bwd"
 C, HW, B = (int(a) for a in sys.argv[2:5]) if len(sys.argv) >= 5 else (256, 3136, 256)
 dt = sys.argv[5] if len(sys.argv) > 5 else "f32"
 pair = int(sys.argv[6]) if len(sys.argv) > 6 else -1
+layout = sys.argv[7] if len(sys.argv) > 7 else "nchw"
 g = 32
 torch.manual_seed(0)
 _lib.lib().gh_set_option(b"gram_fwd_pair", pair)
@@ -20,6 +21,9 @@ if kind in ("bwd", "fwd"):
     x = torch.relu(torch.randn(B, C, HW, device="cuda"))
     if dt == "bf16":
         x = x.bfloat16()
+    if layout == "nhwc":                       # what a channels_last backbone hands over
+        side = int(round(HW ** 0.5))
+        x = x.view(B, C, side, side).contiguous(memory_format=torch.channels_last)
     desc = torch.empty(B, 1, g * g, device="cuda")
     dd = torch.randn(B, 1, g * g, device="cuda")
     for _ in range(4):
@@ -33,4 +37,4 @@ else:
     for _ in range(4):
         ops.gemm_f32(a, w.t())
 torch.cuda.synchronize()
-print("done", kind, C, HW, B, dt, pair)
+print("done", kind, C, HW, B, dt, pair, layout)

@@ -57,11 +57,18 @@ def launch_shares(tag):
     print("\n".join(lines[:12]))
 
 
+ALGO = {}
+
+
 def rep_summary(tag, name):
     rep = os.path.join(OUT, f"{tag}_{name}.ncu-rep")
-    if not os.path.isfile(rep):
+    exported = os.path.join(OUT, f"{tag}_{name}_raw.csv")          # the visit scripts export on the box and drop the .ncu-rep
+    if os.path.isfile(rep):
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    elif os.path.isfile(exported):
+        raw = open(exported).read()
+    else:
         return {}
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
@@ -69,7 +76,7 @@ def rep_summary(tag, name):
     traffic = {}
     for r in rows[2:]:
         kname = r[idx["Kernel Name"]]
-        lines.append(f"\n== {kname}")
+        lines.append(f"\n== {kname}   [{name}]")
         for k in RAW_KEYS:
             if k in idx:
                 lines.append(f"{k:85s} {r[idx[k]]:>18s} {units[idx[k]]}")
@@ -79,6 +86,18 @@ def rep_summary(tag, name):
                 u = units[idx[key]].lower()
                 return v * {"gbyte": 1e9, "mbyte": 1e6, "kbyte": 1e3, "byte": 1.0}.get(u, 1.0)
             traffic[kname] = int(val("dram__bytes_read.sum") + val("dram__bytes_write.sum"))
+            m = re.match(r"(fwd|bwd)_(\d+)_(\d+)_(f32|bf16)_(nchw|nhwc)", name)     # capture names carry the bench's key
+            if m:
+                dt = "torch.float32" if m.group(4) == "f32" else "torch.bfloat16"
+                tail = ",nhwc" if m.group(5) == "nhwc" else ""
+                key = f"gram_pool_{m.group(1)}[C={m.group(2)},HW={m.group(3)},{dt}{tail}]"
+                traffic[key] = traffic[kname]
+                # algorithmic bytes of the captured launch (tools/prof_one.py: batch 256, g 32), so that bench.py can
+                # scale the measured traffic to launches of another batch size (every image is streamed once)
+                c, hw, sz = int(m.group(2)), int(m.group(3)), (4 if m.group(4) == "f32" else 2)
+                per_image = c * hw * sz + 32 * 32 * 4 + (c * hw * 4 if m.group(1) == "bwd" else 0)
+                ALGO[key] = 256 * per_image
+                traffic[f"{kname} [C={m.group(2)},HW={m.group(3)},{m.group(5)}]"] = traffic.pop(kname)
         except Exception:
             pass
     open(os.path.join(PROF, f"{tag}_{name}_ncu_summary.txt"), "w").write("\n".join(lines) + "\n")
@@ -107,6 +126,7 @@ def main():
         path = os.path.join(PROF, "ncu_traffic.json")
         old = json.load(open(path)) if os.path.isfile(path) else {}
         old.update(mapped)
+        old.setdefault("_algorithmic_bytes_of_captured_launch", {}).update(ALGO)
         json.dump(old, open(path, "w"), indent=1, sort_keys=True)
         print("traffic:", mapped)
 
