@@ -11,6 +11,7 @@
 #include "umma_gemm.cuh"
 #include "preprocess.cuh"
 #include "transpose.cuh"
+#include "patchgan.cuh"
 #include <string>
 
 namespace gh {
@@ -626,6 +627,69 @@ int gh_gemm_f32(const float* A, long long a_sm, long long a_sk, const float* Bm,
                 const float* bias, float* D, long long ldd, int M, int N, int K, void* stream) {
   if (!A || !Bm || !D || M <= 0 || N <= 0 || K <= 0) return GH_ERR_BAD_ARG;
   return (int)gemm_auto(A, a_sm, a_sk, Bm, b_sk, b_sn, bias, D, ldd, M, N, K, 0, (cudaStream_t)stream);
+}
+
+long long gh_patch_gram_workspace(int L, int B, int D) {
+  if (L <= 0 || B <= 0 || D <= 0) return 0;
+  return (long long)L * B * D * (kPatchBins + 4);      // bin means (16 floats) + two doubles per plane
+}
+
+int gh_patch_gram_fwd(const float* const* maps, const int* H, const int* W, const long long* strides, int L, int B,
+                      int D, int ln_input, float* gram, float* gram_norm, float* workspace, void* stream) {
+  if (!maps || !H || !W || !strides || !gram || !gram_norm || !workspace || L <= 0 || B <= 0 || D <= 0)
+    return GH_ERR_BAD_ARG;
+  if ((uintptr_t)workspace % 8 != 0) return GH_ERR_BAD_ARG;
+  if (L > kPatchMaxLayers || D > kPatchMaxD || B > 0x7fffffff / 2) return GH_ERR_UNSUPPORTED;
+  PatchGramParams p{};
+  for (int l = 0; l < L; ++l) {
+    if (!maps[l] || H[l] <= 0 || W[l] <= 0) return GH_ERR_BAD_ARG;
+    p.layer[l].x = maps[l];
+    p.layer[l].H = H[l];
+    p.layer[l].W = W[l];
+    p.layer[l].s_img = strides[4 * l + 0];
+    p.layer[l].s_c = strides[4 * l + 1];
+    p.layer[l].s_y = strides[4 * l + 2];
+    p.layer[l].s_x = strides[4 * l + 3];
+  }
+  p.L = L; p.B = B; p.D = D; p.ln_input = ln_input ? 1 : 0;
+  p.gram = gram; p.gram_norm = gram_norm;
+  const long long planes = (long long)L * B * D;
+  double* stats = reinterpret_cast<double*>(workspace);              // (L, B, D, 2) doubles first: 8 B aligned
+  float* pooled = workspace + planes * 4;                            // (L, B, D, 16)
+  const long long gx = (long long)B * ((D + 7) / 8);
+  if (gx > 0x7fffffffLL) return GH_ERR_UNSUPPORTED;
+  patch_pool_kernel<<<dim3((unsigned)gx, L), kPatchThreads, 0, (cudaStream_t)stream>>>(p, pooled, stats);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  const size_t smem = (size_t)D * kPatchBins * 4 + 32 * sizeof(double);
+  patch_gram_kernel<<<dim3(B, L), kPatchThreads, smem, (cudaStream_t)stream>>>(p, pooled, stats);
+  return (int)cudaGetLastError();
+}
+
+int gh_patch_attn_fwd(const float* feat, const float* W_in1, const float* b_in1, const float* W_out1,
+                      const float* b_out1, const float* W_in2, const float* b_in2, const float* W_out2,
+                      const float* b_out2, const float* W_c, const float* b_c, int L, int B, int E, int heads, int nc,
+                      float* emb, float* logits, void* stream) {
+  if (!feat || !W_in1 || !b_in1 || !W_out1 || !b_out1 || !W_in2 || !b_in2 || !W_out2 || !b_out2 || !W_c || !b_c ||
+      !emb || !logits)
+    return GH_ERR_BAD_ARG;
+  if (L <= 0 || B <= 0 || E <= 0 || heads <= 0 || nc <= 0 || E % heads != 0) return GH_ERR_BAD_ARG;
+  if (L > kPatchMaxLayers || E > 128 || E % 4 != 0) return GH_ERR_UNSUPPORTED;
+  const float* ptrs[6] = {W_in1, W_out1, W_in2, W_out2, feat, W_c};
+  for (int i = 0; i < 4; ++i)
+    if ((uintptr_t)ptrs[i] % 16 != 0) return GH_ERR_UNSUPPORTED;       // weight rows are read as float4
+  PatchAttnParams p{};
+  p.feat = feat;
+  p.w_in[0] = W_in1; p.b_in[0] = b_in1; p.w_out[0] = W_out1; p.b_out[0] = b_out1;
+  p.w_in[1] = W_in2; p.b_in[1] = b_in2; p.w_out[1] = W_out2; p.b_out[1] = b_out2;
+  p.w_c = W_c; p.b_c = b_c;
+  p.L = L; p.B = B; p.E = E; p.heads = heads; p.nc = nc;
+  p.emb = emb; p.logits = logits;
+  const size_t smem = ((size_t)L * E * 5 + (size_t)heads * L * L) * 4;
+  const int sms = gh_sm_count();
+  const int grid = B < 4 * sms ? B : 4 * sms;
+  patch_attention_kernel<<<grid, kPatchThreads, smem, (cudaStream_t)stream>>>(p);
+  return (int)cudaGetLastError();
 }
 
 long long gh_attn_head_bwd_workspace(int B, int L, int E) {

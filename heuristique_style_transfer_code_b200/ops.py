@@ -242,6 +242,63 @@ def gemm_f32(a: torch.Tensor, b: torch.Tensor, bias: torch.Tensor = None) -> tor
     return out
 
 
+def patch_gram(maps: Sequence[torch.Tensor], ln_input: bool = True):
+    """The L collected (B, D, H_l, W_l) fp32 maps of one Multi-PatchGAN discriminator -> (gram (L, B, D*D),
+    gram_norm (L, B)) through gh_patch_gram_fwd: [layer norm over the map,] 4x4 adaptive average pooling, layer norm,
+    Gram over the 16 positions / (16 + 1e-6), Frobenius norm (Models_Multi_PatchGAN.py:198, :210-223)."""
+    import ctypes
+    L = len(maps)
+    if L == 0:
+        raise GramHeadError("gramhead: patch_gram needs at least one feature map")
+    for m in maps:
+        _require_cuda(m, "feature map")
+        if m.dtype != torch.float32 or m.dim() != 4 or m.shape[:2] != maps[0].shape[:2] or m.device != maps[0].device:
+            raise GramHeadError("gramhead: patch_gram takes fp32 (B, D, H, W) maps with one B, D and device")
+    b, d = maps[0].shape[:2]
+    dev = maps[0].device
+    gram = torch.empty((L, b, d * d), device=dev, dtype=torch.float32)
+    norm = torch.empty((L, b), device=dev, dtype=torch.float32)
+    scratch = torch.empty((_lib.lib().gh_patch_gram_workspace(L, b, d) + 1) // 2, device=dev, dtype=torch.float64)
+    ptrs = (ctypes.c_void_p * L)(*[m.data_ptr() for m in maps])
+    hs = (ctypes.c_int * L)(*[m.shape[2] for m in maps])
+    ws = (ctypes.c_int * L)(*[m.shape[3] for m in maps])
+    st = (ctypes.c_longlong * (4 * L))(*[v for m in maps for v in m.stride()])
+    work = dict(bytes=sum(m.numel() for m in maps) * 4 + gram.numel() * 4, flops=2 * L * b * d * d * 16, kind="patch_gram")
+    with torch.cuda.device(dev), _Timed(f"patch_gram[L={L},D={d},HW0={maps[0].shape[2]}x{maps[0].shape[3]}]", 2, dev, **work):
+        rc = _lib.lib().gh_patch_gram_fwd(ptrs, hs, ws, st, L, b, d, 1 if ln_input else 0, gram.data_ptr(),
+                                          norm.data_ptr(), scratch.data_ptr(), _stream_ptr(maps[0]))
+    check(rc, "gh_patch_gram_fwd")
+    return gram, norm
+
+
+def patch_attention(feat: torch.Tensor, attn1: torch.nn.MultiheadAttention, attn2: torch.nn.MultiheadAttention,
+                    classifier: torch.nn.Linear):
+    """feat (L, B, E) -> (embeddings (B, E), output (B, nc)): the two multi-head attentions over the layer tokens, the
+    mean over layers and the classifier (Models_Multi_PatchGAN.py:243-256) in one launch (gh_patch_attn_fwd)."""
+    _require_cuda(feat, "feat")
+    L, b, e = feat.shape
+    feat = feat.contiguous()
+    nc = classifier.out_features
+    emb = torch.empty((b, e), device=feat.device, dtype=torch.float32)
+    out = torch.empty((b, nc), device=feat.device, dtype=torch.float32)
+    tensors = []
+    for a in (attn1, attn2):
+        if a.in_proj_weight is None or a.in_proj_bias is None or a.embed_dim != e or a.num_heads != attn1.num_heads:
+            raise GramHeadError("gramhead: patch_attention needs packed in_proj weights with biases and one embed_dim")
+        tensors += [a.in_proj_weight, a.in_proj_bias, a.out_proj.weight, a.out_proj.bias]
+    tensors += [classifier.weight, classifier.bias]
+    tensors = [t.detach().contiguous() for t in tensors]
+    for t in tensors:
+        _require_cuda(t, "head parameter")
+    work = dict(bytes=(feat.numel() + emb.numel() + out.numel() + sum(t.numel() for t in tensors)) * 4,
+                flops=2 * b * L * (2 * 4 * e * e) + 2 * b * e * nc, kind="patch_attention")
+    with torch.cuda.device(feat.device), _Timed(f"patch_attention[L={L},E={e}]", 1, feat.device, **work):
+        rc = _lib.lib().gh_patch_attn_fwd(feat.data_ptr(), *[t.data_ptr() for t in tensors], L, b, e, attn1.num_heads, nc,
+                                          emb.data_ptr(), out.data_ptr(), _stream_ptr(feat))
+    check(rc, "gh_patch_attn_fwd")
+    return emb, out
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # autograd
 # ----------------------------------------------------------------------------------------------------------------------

@@ -131,6 +131,38 @@ int gh_preprocess_frame(const unsigned char* frame, long long pitch_bytes, int H
 int gh_gemm_f32(const float* A, long long a_sm, long long a_sk, const float* B, long long b_sk, long long b_sn,
                 const float* bias, float* D, long long ldd, int M, int N, int K, void* stream);
 
+/* ---- Gram head of the Multi-PatchGAN discriminator (the *_test classes of Models/Models_Multi_PatchGAN.py) ----------
+ * gh_patch_gram_fwd replaces, for all L collected feature maps of one discriminator in one launch,
+ *   F.layer_norm(x_proj, x_proj.shape[1:])                  :198   (only when ln_input != 0; otherwise pass the
+ *                                                                    already normalised maps of :199)
+ *   F.adaptive_avg_pool2d(feature_map, (4, 4))              :210
+ *   F.layer_norm(pooled, pooled.shape[1:])                  :213
+ *   torch.bmm(fm, fm^T) / (16 + 1e-6)                       :217-220
+ *   torch.norm(gram, p='fro', dim=(1, 2))                   :223
+ * maps[l]: device pointer to layer l's (B, D, H[l], W[l]) fp32 map; strides[4*l..4*l+3] = its image / channel / row /
+ * column strides in elements (any layout; NCHW is the coalesced one). maps, H, W, strides are HOST arrays of length L
+ * (4L for strides). L <= 8, D <= 128 (GH_ERR_UNSUPPORTED beyond). gram: (L, B, D*D) row-major flattened as :226 does;
+ * gram_norm: (L, B).
+ * workspace: gh_patch_gram_workspace(L, B, D) fp32 elements, 8 B aligned (bin means and per-channel sums between the two
+ * launches: a pooling pass with one warp per channel plane, then one CTA per (image, layer) for the norms and the Gram). */
+long long gh_patch_gram_workspace(int L, int B, int D);
+int gh_patch_gram_fwd(const float* const* maps, const int* H, const int* W, const long long* strides, int L, int B,
+                      int D, int ln_input, float* gram, float* gram_norm, float* workspace, void* stream);
+
+/* gh_patch_attn_fwd replaces
+ *   attention_per_layer(x, x, x), attention_per_patch(y, y, y)   :243-244  (nn.MultiheadAttention(ndf, heads), sequence =
+ *                                                                           the L layers, dropout 0, no masks)
+ *   torch.mean(..., dim=0)                                       :247
+ *   self.classifier(aggregated_features)                         :256
+ * feat: (L, B, E) projected Gram features (the stack of :240; the Linear of :229 is gh_gemm_f32 over the L*B rows of
+ * gh_patch_gram_fwd's output). W_in* (3E, E), b_in* (3E), W_out* (E, E), b_out* (E): in_proj_weight / in_proj_bias /
+ * out_proj.weight / out_proj.bias of the two attention modules; W_c (nc, E), b_c (nc). emb: (B, E) `embeddings`,
+ * logits: (B, nc) `output`. L <= 8, E <= 128, E % 4 == 0, E % heads == 0, 16 B-aligned weights. */
+int gh_patch_attn_fwd(const float* feat, const float* W_in1, const float* b_in1, const float* W_out1,
+                      const float* b_out1, const float* W_in2, const float* b_in2, const float* W_out2,
+                      const float* b_out2, const float* W_c, const float* b_c, int L, int B, int E, int heads, int nc,
+                      float* emb, float* logits, void* stream);
+
 /* Number of fp32 elements gh_attn_head_bwd needs in `workspace`. */
 long long gh_attn_head_bwd_workspace(int B, int L, int E);
 

@@ -77,3 +77,10 @@ def load_reference_functions():
         raise FileNotFoundError(REFERENCE_ROOT)
     _stub_gui_modules()
     return _load("functions/functions_RESNET50_Truncate_Gram_Attention.py", "_ref_functions_gram_attention")
+
+
+def load_reference_patchgan():
+    """Models/Models_Multi_PatchGAN.py (imports only torch); the *_test classes carry the Gram head."""
+    if not reference_available():
+        raise FileNotFoundError(REFERENCE_ROOT)
+    return _load("Models/Models_Multi_PatchGAN.py", "_ref_models_multi_patchgan")

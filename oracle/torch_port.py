@@ -61,3 +61,45 @@ class PortModel(nn.Module):
             return torch.zeros((x.size(0), self.num_classes), requires_grad=True).to(self.device)
         emb, logits = head(outs, self.gram_matrix_size, self.attention, self.classifier)
         return (emb, logits) if self.return_embeddings else logits
+
+
+def patchgan_forward(model, x: torch.Tensor):
+    """fp32 torch restatement of VariablePatchesNLayerDiscriminator_test.forward (Models/Models_Multi_PatchGAN.py:177-258),
+    op for op, on the submodules of `model` (any module with the reference's attribute names: the reference class or this
+    repo's drop-in), on whatever device they live. Returns (embeddings, output, gram_norms list)."""
+    collected, k = [], 0
+    for idx, layer in enumerate(model.feature_extractor):
+        x = layer(x)
+        if torch.isnan(x).any():
+            print(f"NaN detected after layer {idx}")
+            x = torch.nan_to_num(x, nan=0.0)
+        if isinstance(layer, nn.Conv2d):
+            proj = model.projection_layers[k](x)
+            k += 1
+            if torch.isnan(proj).any():
+                print(f"NaN detected in projected feature map at layer {idx}")
+                proj = torch.nan_to_num(proj, nan=0.0)
+            collected.append(F.layer_norm(proj, proj.shape[1:]))
+    tokens, norms = [], []
+    for i, fm in enumerate(collected):
+        pooled = F.adaptive_avg_pool2d(fm, output_size=(4, 4))
+        pooled = F.layer_norm(pooled, pooled.shape[1:])
+        flat = pooled.view(pooled.size(0), model.gram_matrix_dim, -1)
+        gram = torch.bmm(flat, flat.transpose(1, 2)) / (flat.size(-1) + 1e-6)
+        norms.append(torch.norm(gram, p='fro', dim=(1, 2)))
+        tok = model.feature_projection(gram.view(gram.size(0), -1))
+        if torch.isnan(tok).any():
+            print(f"NaN detected in projected features at layer {i}, replacing NaNs with zeros.")
+            tok = torch.nan_to_num(tok, nan=0.0)
+        tokens.append(tok)
+    seq = torch.stack(tokens, dim=0)
+    seq, _ = model.attention_per_layer(seq, seq, seq)
+    seq, _ = model.attention_per_patch(seq, seq, seq)
+    emb = seq.mean(dim=0)
+    return emb, model.classifier(emb), norms
+
+
+def patchgan_multiscale_forward(model, x: torch.Tensor):
+    """MultiScaleDiscriminator_test.forward (:299-312): every scale sees the same input; plain means over the scales."""
+    embs, outs = zip(*[patchgan_forward(d, x)[:2] for d in model.scale_discriminators.values()])
+    return torch.stack(embs, 0).mean(0), torch.stack(outs, 0).mean(0)
