@@ -150,6 +150,48 @@ def summarise_profile(records, peaks):
     return kernels, roof
 
 
+def patchgan_leg(device, peaks, steps, batch=64):
+    """MultiScaleDiscriminator_test (ndf 64, gram_matrix_dim 64, batch norm, patches 10/70/150) on `batch` 224x224 images:
+    this repo's classes (cuDNN extractor + the library's head kernels) and the op-for-op torch port of the reference
+    forward, same GPU, same weights, eval + no_grad. The head's dominant kernel is the pooling pass (HBM-bound)."""
+    from heuristique_style_transfer_code_b200 import ops
+    from heuristique_style_transfer_code_b200.patchgan import MultiScaleDiscriminator_test
+    from oracle.torch_port import patchgan_multiscale_forward
+    torch.manual_seed(0)
+    m = MultiScaleDiscriminator_test(ndf=64, norm='batch', num_classes=NUM_CLASSES, gram_matrix_dim=64).to(device).eval()
+    x = torch.randn(batch, 3, IMAGE, IMAGE, device=device)
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(device)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            fn()
+        e.record()
+        torch.cuda.synchronize(device)
+        return s.elapsed_time(e) / steps
+
+    with torch.no_grad():
+        ours = timed(lambda: m(x))
+        port = timed(lambda: patchgan_multiscale_forward(m, x))
+        saved, ops.PROFILE = ops.PROFILE, []
+        for _ in range(steps):
+            e1, o1 = m(x)
+        torch.cuda.synchronize(device)
+        rec, ops.PROFILE = ops.PROFILE, saved
+        e2, o2 = patchgan_multiscale_forward(m, x)
+    kernels, roof = summarise_profile(rec, peaks)
+    head_ms = sum(k["total_ms"] for k in kernels.values()) / steps
+    return {"workload": f"MultiScaleDiscriminator_test ndf 64, gram_matrix_dim 64, 3 scales, batch {batch} at {IMAGE}x{IMAGE}, "
+                        "eval/no_grad", "images_per_s": round(batch / ours * 1e3, 1), "ms_per_step": round(ours, 3),
+            "torch_port_same_gpu_ms": round(port, 3), "torch_port_images_per_s": round(batch / port * 1e3, 1),
+            "head_kernels_ms": round(head_ms, 3), "embeddings_rel_diff_vs_port": float((e1 - e2).norm() / e2.norm()),
+            "output_rel_diff_vs_port": float((o1 - o2).norm() / o2.norm()),
+            "argmax_equal": bool((o1.argmax(1) == o2.argmax(1)).all()), "kernels": kernels, "roofline": roof}
+
+
 def cpu_reference_forward(batch, sample, steps, warmup, threads):
     """The reference's CPU path (oracle port), eval + no_grad, on `sample` images of the synthetic batch."""
     from torchvision import models
@@ -299,6 +341,12 @@ def run_ours(args):
                    "logits_rel_diff_vs_fp32_backbone": float((lg_fast.float() - lg_ref).norm() / lg_ref.norm()),
                    "argmax_equal": bool((lg_fast.argmax(1) == lg_ref.argmax(1)).all())}
 
+    # ---- Multi-PatchGAN discriminators (MultiScaleDiscriminator_test) with the Gram head on this library,
+    # against the fp32 torch port of the reference forward on the same GPU and weights; reported beside the headline.
+    patchgan = None
+    if not args.skip_patchgan and rank == 0:
+        patchgan = patchgan_leg(device, peaks, max(3, args.steps // 4))
+
     # ---- configs[2]: training step, global batch 512 over the ranks (strong scaling), AdamW ----
     train = None
     if not args.skip_train:
@@ -371,6 +419,7 @@ def run_ours(args):
             "breakdown": {"encoder_cudnn_ms": round(enc_ms, 3), "head_ms": round(head_ms, 3),
                           "head_images_per_s": round(B / (head_ms / 1e3), 1), "kernels": kernels},
             "backbone_handoff": handoff,
+            "patchgan_head": patchgan,
             "train": train}
     emit(json.dumps(line))
 
@@ -408,6 +457,7 @@ def main():
     ap.add_argument("--skip-train", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-handoff", action="store_true")
+    ap.add_argument("--skip-patchgan", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
