@@ -296,19 +296,24 @@ def run_ours(args):
 
     # ---- end to end through the public API: pinned host batches in, logits + embeddings back on the host ----
     # The loop is the package's evaluation loop shape (functions.evaluate_model_test): cuda_prefetch uploads batch i+1
-    # on a side stream while batch i is in the model; every step's H2D copy and D2H read are inside the timed region.
-    from heuristique_style_transfer_code_b200.functions import cuda_prefetch
+    # on a side stream while batch i is in the model and HostCollector brings every step's embeddings + logits back
+    # into pinned host memory without a per-step synchronisation; every step's H2D copy and D2H read are inside the
+    # timed region, which ends only when the last step's results are on the host.
+    from heuristique_style_transfer_code_b200.functions import HostCollector, cuda_prefetch
 
     def e2e_loop(n):
+        results = HostCollector()
         with torch.no_grad():
             for (xb,) in cuda_prefetch(((x_host,) for _ in range(n)), device):
                 emb, logits = model(xb)
                 if world > 1:
                     logits = D.gather_rows(logits, total, world)
                     emb = D.gather_rows(emb, total, world)
-                emb.cpu(), logits.cpu()                 # D2H of the results (the synchronisation point, as upstream)
+                results.push(emb, logits)             # D2H of this step's results into pinned host memory
+        out = results.finish()                        # every step's results are on the host when the region ends
+        assert len(out) == n and out[-1][1].shape == (total, NUM_CLASSES)
 
-    e2e_loop(2)
+    e2e_loop(3)
     e2e_ms = timed_region(lambda: e2e_loop(args.steps), 1, device, D)
     e2e_value = total * args.steps / (e2e_ms / 1e3)
     h2d = B * 3 * IMAGE * IMAGE * 4
@@ -332,7 +337,19 @@ def run_ours(args):
             _, lg_ref = model(x)
             model.set_backbone_mode(default_mode)
             _, lg_def = model(x)
-        handoff = {"default_mode": default_mode,
+            model.fold_batchnorm = False                 # children executed one by one, as the reference does
+            for _ in range(2):
+                infer_step()
+            nsteps = max(3, args.steps // 4)
+            ums = timed_region(infer_step, nsteps, device, D) / nsteps
+            _, lg_unf = model(x)
+            model.fold_batchnorm = True
+        handoff = {"default_mode": default_mode + (" + folded eval-mode batch norm (cuDNN conv+bias+ReLU epilogues)"
+                                                   if model._plan is not None else ""),
+                   "default_vs_unfolded_logits_rel_diff": float((lg_def - lg_unf).norm() / lg_unf.norm()),
+                   "default_vs_unfolded_argmax_equal": bool((lg_def.argmax(1) == lg_unf.argmax(1)).all()),
+                   "unfolded_channels_last_ms_per_step": round(ums, 3),
+                   "unfolded_channels_last_images_per_s": round(total / (ums / 1e3), 1),
                    "default_vs_nchw_logits_rel_diff": float((lg_def - lg_ref).norm() / lg_ref.norm()),
                    "nchw_reference_mode_ms_per_step": round(rms, 3),
                    "nchw_reference_mode_images_per_s": round(total / (rms / 1e3), 1),
@@ -404,8 +421,9 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": total, "per_gpu_batch": B, "image": IMAGE,
                        "truncate_layer": TRUNC, "gram_matrix_size": GRAM_SIZE, "num_classes": NUM_CLASSES,
-                       "precision": "encoder: cuDNN fp32 in channels_last (TF32 conv allowed, torch default; logits within 1e-7 of "
-                                    "the NCHW execution); Gram forward and backward (tcgen05, "
+                       "precision": "encoder: cuDNN fp32 convolutions in channels_last (TF32 conv allowed, torch default), eval-mode "
+                                    "batch norm folded into them and ReLU / residual add as cuDNN epilogues (same function; "
+                                    "backbone_handoff reports the difference to the unfolded and NCHW executions); Gram forward and backward (tcgen05, "
                                     "fp32 accumulate): tf32 operands, rounded to nearest by the TMA unit (TFLOAT32 tensor "
                                     "maps); attention/classifier: split-bf16 x3 (fp32-accurate)",
                        "l2_policy": "inputs larger than L2 (154 MB images, 210/105/51 MB stage activations per step)",

@@ -135,6 +135,61 @@ def cuda_prefetch(batches, device):
         yield current
 
 
+class HostCollector:
+    """Brings per-batch results to the host without stopping the GPU after every batch.
+
+    The reference reads each batch's outputs with `.cpu().numpy()` (functions:196-199), a device synchronisation per
+    batch: the host cannot queue batch i+1 before batch i has finished, so the GPU idles while Python launches the next
+    forward. push() instead enqueues non-blocking copies into a small ring of pinned buffers and records an event;
+    a slot is only waited for when it comes up for reuse, `depth` batches later (by then its copy is long done), and its
+    content is then moved to ordinary host memory. finish() drains the ring. On CPU tensors it degenerates to a list."""
+
+    def __init__(self, depth: int = 4):
+        self.depth, self.slots, self.count, self.done = depth, [], 0, []
+
+    def _retire(self, slot):
+        bufs, shapes, event = slot
+        if event is not None:
+            event.synchronize()
+        self.done.append(tuple(np.array(b[:n].numpy()) for b, n in zip(bufs, shapes)))
+
+    def push(self, *tensors):
+        if not tensors[0].is_cuda:
+            self.done.append(tuple(t.detach().cpu().numpy() for t in tensors))
+            return
+        i = self.count % self.depth
+        self.count += 1
+        if i < len(self.slots) and self.slots[i] is not None and self.slots[i][2] is not None:
+            self._retire(self.slots[i])
+        rows = [t.shape[0] for t in tensors]
+        reuse = i < len(self.slots) and self.slots[i] is not None and all(
+            b.shape[0] >= t.shape[0] and b.shape[1:] == t.shape[1:] and b.dtype == t.dtype
+            for b, t in zip(self.slots[i][0], tensors))
+        bufs = self.slots[i][0] if reuse else tuple(torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in tensors)
+        for b, t in zip(bufs, tensors):
+            b[:t.shape[0]].copy_(t.detach(), non_blocking=True)
+        event = torch.cuda.Event()
+        event.record(torch.cuda.current_stream(tensors[0].device))
+        slot = (bufs, rows, event)
+        if i < len(self.slots):
+            self.slots[i] = slot
+        else:
+            self.slots.append(slot)
+
+    def finish(self):
+        """-> list of per-batch tuples of numpy arrays, in push order."""
+        if self.slots:
+            n = len(self.slots)
+            start = self.count % self.depth if self.count >= self.depth else 0
+            for k in range(n):
+                slot = self.slots[(start + k) % n]
+                if slot is not None and slot[2] is not None:
+                    self._retire(slot)
+            self.slots = []
+        out, self.done, self.count = self.done, [], 0
+        return out
+
+
 def train_model(model, train_loader, criterion, optimizer, num_epochs=25, writer=None, fold=0):
     """SGD loop of the train script (:123-145): per batch zero_grad / forward / loss / backward / step, a loss print per
     batch, the sample-weighted epoch loss printed and logged as Fold_{fold}/Train/Loss. Returns the model."""
@@ -196,24 +251,24 @@ def evaluate_model_test(model, data_loader, device):
     Image paths are recovered from batch_idx * loader.batch_size, i.e. the loader must not shuffle (as in the reference).
     """
     model.eval()
-    emb_all, prob_all, pred_all, label_all, paths = [], [], [], [], []
+    paths = []
     dataset = data_loader.dataset
+    results = HostCollector()
     with torch.no_grad():
         for batch_idx, (inputs, labels) in enumerate(cuda_prefetch(data_loader, device)):
             embeddings, outputs = model(inputs)
             probs = F.softmax(outputs, dim=1)
             preds = outputs.argmax(dim=1)
-            emb_all.append(embeddings.cpu().numpy())
-            prob_all.append(probs.cpu().numpy())
-            pred_all.extend(preds.cpu().numpy())
-            label_all.extend(labels.cpu().numpy())
+            results.push(embeddings, probs, preds, labels)      # no per-batch synchronisation (the reference's .cpu())
             first = batch_idx * data_loader.batch_size
             for j in range(inputs.size(0)):
                 if isinstance(dataset, Subset):
                     paths.append(dataset.dataset.samples[dataset.indices[first + j]][0])
                 else:
                     paths.append(dataset.samples[first + j][0])
-    return (np.concatenate(emb_all, axis=0), np.array(pred_all), np.array(label_all),
+    batches = results.finish()
+    emb_all, prob_all, pred_all, label_all = ([b[k] for b in batches] for k in range(4))
+    return (np.concatenate(emb_all, axis=0), np.concatenate(pred_all, axis=0), np.concatenate(label_all, axis=0),
             np.concatenate(prob_all, axis=0), paths)
 
 

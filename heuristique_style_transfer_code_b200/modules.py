@@ -20,6 +20,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from .frozen_encoder import FoldedEncoder, encoder_signature
 
 # How the cuDNN backbone hands its stage activations to the head:
 #   "reference"          - exactly the reference's execution: fp32 NCHW, torch defaults (the default on CPU)
@@ -33,6 +34,10 @@ from . import ops
 # the environment variable GRAMHEAD_BACKBONE for unmodified reference scripts (GRAMHEAD_BACKBONE=reference restores
 # the NCHW execution).
 BACKBONE_MODES = ("reference", "channels_last", "bf16", "bf16_channels_last")
+# Inference plan (frozen_encoder.py): in the two channels_last modes, with the module in eval mode and gradients disabled,
+# eval-mode batch norm is folded into the convolution before it and ReLU / residual add run as cuDNN epilogues -- the
+# same function, the same cuDNN convolutions, without the element-wise passes that are 69 % of the encoder's time.
+# model.fold_batchnorm = False (or GRAMHEAD_FOLD_BN=0) executes the children one by one as the reference does.
 
 
 class GramAttentionHead:
@@ -55,6 +60,8 @@ class _TruncatedGramAttentionBase(nn.Module):
         self.classifier = nn.Linear(self.gram_matrix_size ** 2, self.num_classes).to(self.device)
         self.attention = nn.MultiheadAttention(embed_dim=self.gram_matrix_size ** 2, num_heads=1).to(self.device)
         self._backbone_mode = "reference"
+        self.fold_batchnorm = os.environ.get("GRAMHEAD_FOLD_BN", "1") != "0"
+        self._plan = None
         on_cuda = torch.device(self.device).type == "cuda"
         env_mode = os.environ.get("GRAMHEAD_BACKBONE", "")
         if env_mode or on_cuda:
@@ -77,8 +84,36 @@ class _TruncatedGramAttentionBase(nn.Module):
         """(b, ch, h, w) -> (b, ch, ch): F F^T / (h*w), differentiable (dense tcgen05 Gram kernels)."""
         return ops.gram_matrix(activations)
 
+    def train(self, mode: bool = True):
+        if mode:
+            self._plan = None              # weights are about to change: the folded copies are rebuilt at the next eval
+        return super().train(mode)
+
+    def refresh_inference_plan(self):
+        """Drops the folded weight copies. Only needed after editing encoder tensors through `.data` (which bypasses
+        the version counters the plan watches); optimizer steps, load_state_dict, .to() and train() are detected."""
+        self._plan = None
+        return self
+
+    def _inference_plan(self, x):
+        """The folded encoder when it computes the same function as the children (see frozen_encoder.py), else None."""
+        if not (self.fold_batchnorm and self._backbone_mode.endswith("channels_last")) or torch.is_grad_enabled():
+            return None
+        enc = self.truncated_encoder
+        if not x.is_cuda or any(m.training for m in enc.modules() if isinstance(m, nn.modules.batchnorm._BatchNorm)):
+            return None
+        dtype = torch.bfloat16 if self._backbone_mode.startswith("bf16") else torch.float32
+        plan = self._plan
+        if plan is None or plan.dtype != dtype or plan.signature != encoder_signature(enc):
+            plan = FoldedEncoder.build(enc, dtype, channels_last=True) if FoldedEncoder.supported(enc) else None
+            self._plan = plan
+        return plan
+
     def _stage_activations(self, x):
         x = x.to(self.device)
+        plan = self._inference_plan(x)
+        if plan is not None:
+            return plan(x)
         if self._backbone_mode == "reference":
             return self._run_encoder(x)
         if self._backbone_mode.endswith("channels_last"):

@@ -240,3 +240,113 @@ def test_style_iteration_graph_matches_eager():
     assert le[0][0] > le[0][-1]                   # the loss goes down
     assert all(abs(a - b) <= 2e-3 * abs(a) for a, b in zip(le[0], le[1]))   # restart reproduces the first run
     assert float((ne - ng).abs().max()) <= 5e-3
+
+
+# ---- inference plan: eval-mode batch norm folded into the convolutions, ReLU / residual add as cuDNN epilogues ----------
+def _randomise_batchnorm(model, seed=11):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    with torch.no_grad():
+        for m in model.truncated_encoder.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                n = m.num_features
+                m.running_mean.copy_(torch.randn(n, generator=g) * 0.2)
+                m.running_var.copy_(torch.rand(n, generator=g) + 0.5)
+                m.weight.copy_(torch.rand(n, generator=g) * 0.5 + 0.5)      # keeps activations bounded over 40 layers
+                m.bias.copy_(torch.randn(n, generator=g) * 0.1)
+
+
+@pytest.mark.parametrize("mode,tf32,tol", [("channels_last", False, 2e-5), ("channels_last", True, 5e-3),
+                                           ("bf16_channels_last", True, 3e-2)])
+def test_folded_inference_plan_matches_the_unfolded_encoder(mode, tf32, tol):
+    from torchvision import models
+    from heuristique_style_transfer_code_b200 import TruncatedResNet50_for_test
+    torch.backends.cudnn.allow_tf32 = tf32
+    try:
+        torch.manual_seed(0)
+        m = TruncatedResNet50_for_test(models.resnet50(weights=None), 7, 4, 32, device="cuda").eval()
+        _randomise_batchnorm(m)
+        m.set_backbone_mode(mode)
+        x = torch.randn(16, 3, 224, 224, device="cuda")
+        with torch.no_grad():
+            m.fold_batchnorm = True
+            e1, l1 = m(x)
+            assert m._plan is not None and m._plan.dtype == (torch.bfloat16 if mode.startswith("bf16") else torch.float32)
+            _, stages1 = m._stage_activations(x)
+            m.fold_batchnorm = False
+            e0, l0 = m(x)
+            _, stages0 = m._stage_activations(x)
+        for a, b in zip(stages1, stages0):
+            assert a.shape == b.shape and a.dtype == b.dtype and a.is_contiguous(memory_format=torch.channels_last)
+            assert O.rel_err(npf(a), npf(b)) <= tol
+        assert O.rel_err(npf(e1), npf(e0)) <= tol and O.rel_err(npf(l1), npf(l0)) <= tol
+        assert (l1.argmax(1) == l0.argmax(1)).all()
+    finally:
+        torch.backends.cudnn.allow_tf32 = False
+
+
+def test_inference_plan_follows_weight_updates_and_is_skipped_when_gradients_are_needed():
+    from torchvision import models
+    from heuristique_style_transfer_code_b200 import TruncatedResNet50
+    torch.manual_seed(0)
+    m = TruncatedResNet50(models.resnet50(weights=None), 6, 4, 32, device="cuda")
+    _randomise_batchnorm(m)
+    x = torch.randn(8, 3, 128, 128, device="cuda")
+    y = torch.randint(0, 4, (8,), device="cuda")
+
+    def both():
+        m.eval()
+        with torch.no_grad():
+            m.fold_batchnorm = True
+            a = m(x)
+            m.fold_batchnorm = False
+            b = m(x)
+            m.fold_batchnorm = True
+        return a, b
+
+    a, b = both()
+    assert O.rel_err(npf(a), npf(b)) <= 2e-5
+    first_plan = m._plan
+    # a training step changes weights and running statistics: the next eval forward must see them
+    m.train()
+    opt = torch.optim.SGD(m.parameters(), lr=0.05)
+    torch.nn.functional.cross_entropy(m(x), y).backward()
+    opt.step()
+    a2, b2 = both()
+    assert m._plan is not first_plan
+    assert O.rel_err(npf(a2), npf(b2)) <= 2e-5 and O.rel_err(npf(a2), npf(a)) > 1e-4
+    # an in-place edit in eval mode (no train() in between) is caught through the tensors' version counters
+    with torch.no_grad():
+        m.truncated_encoder[4][0].bn1.weight.mul_(1.5)
+    a3, b3 = both()
+    assert O.rel_err(npf(a3), npf(b3)) <= 2e-5 and O.rel_err(npf(a3), npf(a2)) > 1e-4
+    # load_state_dict too
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    sd["truncated_encoder.0.weight"] = sd["truncated_encoder.0.weight"] * 0.5
+    m.load_state_dict(sd)
+    a4, b4 = both()
+    assert O.rel_err(npf(a4), npf(b4)) <= 2e-5 and O.rel_err(npf(a4), npf(a3)) > 1e-4
+    # with gradients enabled (style transfer differentiates through the eval-mode encoder) the children run as before
+    m.eval()
+    xg = x.clone().requires_grad_(True)
+    m(xg).sum().backward()
+    assert xg.grad is not None and torch.isfinite(xg.grad).all()
+    # the reference (NCHW) mode never folds
+    m.set_backbone_mode("reference")
+    with torch.no_grad():
+        m(x)
+    assert m._inference_plan(x) is None
+
+
+def test_host_collector_keeps_order_with_ragged_batches():
+    from heuristique_style_transfer_code_b200.functions import HostCollector
+    c = HostCollector(depth=3)
+    sizes = [5, 5, 5, 5, 5, 5, 5, 2]
+    for i, n in enumerate(sizes):
+        a = torch.full((n, 7), float(i), device="cuda")
+        b = torch.arange(n, device="cuda") + 100 * i
+        c.push(a * 2, b)                      # temporaries: the copy must be ordered after the producer on the stream
+    out = c.finish()
+    assert [o[0].shape[0] for o in out] == sizes
+    for i, (a, b) in enumerate(out):
+        assert (a == 2.0 * i).all() and (b == np.arange(sizes[i]) + 100 * i).all()
+    assert c.finish() == []
