@@ -304,7 +304,7 @@ def run_ours(args):
     def e2e_loop(n):
         results = HostCollector()
         with torch.no_grad():
-            for (xb,) in cuda_prefetch(((x_host,) for _ in range(n)), device):
+            for (xb,) in cuda_prefetch(((x_host,) for _ in range(n)), device, reuse_buffers=True):
                 emb, logits = model(xb)
                 if world > 1:
                     logits = D.gather_rows(logits, total, world)

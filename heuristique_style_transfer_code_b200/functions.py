@@ -97,24 +97,64 @@ def _default_device():
     return torch.device('cuda' if torch.cuda.is_available() else 'cpu')
 
 
-def cuda_prefetch(batches, device):
+_COPY_STREAMS = {}
+
+
+def _copy_stream(device):
+    """One upload stream per device for the life of the process: the caching allocator keeps a block pool per stream,
+    so a fresh stream per loop would strand the previous loop's staging buffers and allocate new ones."""
+    key = (device.type, torch.cuda.current_device() if device.index is None else device.index)
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _COPY_STREAMS[key]
+
+
+def cuda_prefetch(batches, device, reuse_buffers=False):
     """Yields the batches of `batches` (tuples / lists of tensors, e.g. a DataLoader) already on `device`.
     On CUDA, batch i+1 is uploaded on a side stream while batch i is being processed, so the host->device copy
     (154 MB for 256 images at 224x224) leaves the critical path; use pin_memory=True loaders for the copy to be
-    asynchronous. The reference moves every batch synchronously inside its loops (functions:129-130, :157-158, :190)."""
+    asynchronous. The reference moves every batch synchronously inside its loops (functions:129-130, :157-158, :190).
+
+    reuse_buffers=True uploads into two fixed sets of device buffers instead of allocating per batch (no allocator
+    traffic, constant memory): a yielded batch is then only valid until the next one is requested -- what loops that
+    consume a batch and move on (this package's train / evaluation loops) need; leave it False when batches are kept."""
     device = torch.device(device)
     if device.type != 'cuda':
         for batch in batches:
             yield tuple(t.to(device) if torch.is_tensor(t) else t for t in batch)
         return
-    copy_stream = torch.cuda.Stream(device=device)
+    copy_stream = _copy_stream(device)
+    slots = [None, None]              # per slot: list of device buffers (one per tensor position of the batch)
+    consumed = [None, None]           # per slot: event on the consumer's stream after its last use of the slot
+    count = 0
+
+    def place(slot, pos, t):
+        if not reuse_buffers:
+            return t.to(device, non_blocking=True)
+        bufs = slots[slot]
+        buf = bufs.get(pos)
+        if buf is None or buf.dtype != t.dtype or buf.shape[1:] != t.shape[1:] or buf.shape[0] < t.shape[0] or t.dim() == 0:
+            if t.dim() == 0:
+                return t.to(device, non_blocking=True)
+            buf = torch.empty(t.shape, dtype=t.dtype, device=device)
+            bufs[pos] = buf
+        view = buf[:t.shape[0]]
+        view.copy_(t, non_blocking=True)
+        return view
 
     def upload(batch):
+        nonlocal count
+        slot = count % 2
+        count += 1
+        if slots[slot] is None:
+            slots[slot] = {}
         with torch.cuda.stream(copy_stream):
-            moved = tuple(t.to(device, non_blocking=True) if torch.is_tensor(t) else t for t in batch)
+            if reuse_buffers and consumed[slot] is not None:
+                copy_stream.wait_event(consumed[slot])       # the batch that last lived in these buffers is done with
+            moved = tuple(place(slot, i, t) if torch.is_tensor(t) else t for i, t in enumerate(batch))
         done = torch.cuda.Event()
         done.record(copy_stream)
-        return moved, done
+        return moved, done, slot
 
     it = iter(batches)
     try:
@@ -122,17 +162,22 @@ def cuda_prefetch(batches, device):
     except StopIteration:
         return
     while pending is not None:
-        current, done = pending
+        current, done, slot = pending
         try:
             pending = upload(next(it))          # queued before the consumer touches `current`: overlaps its compute
         except StopIteration:
             pending = None
         main = torch.cuda.current_stream(device)
         main.wait_event(done)
-        for t in current:
-            if torch.is_tensor(t):
-                t.record_stream(main)
+        if not reuse_buffers:
+            for t in current:
+                if torch.is_tensor(t):
+                    t.record_stream(main)
         yield current
+        if reuse_buffers:                       # the consumer has queued everything that reads `current`
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(device))
+            consumed[slot] = ev
 
 
 class HostCollector:
@@ -199,7 +244,7 @@ def train_model(model, train_loader, criterion, optimizer, num_epochs=25, writer
     n_batches = len(train_loader)
     for epoch in range(num_epochs):
         running = 0.0
-        for step, (inputs, labels) in enumerate(cuda_prefetch(train_loader, device)):
+        for step, (inputs, labels) in enumerate(cuda_prefetch(train_loader, device, reuse_buffers=True)):
             optimizer.zero_grad()
             loss = criterion(model(inputs), labels)
             loss.backward()
@@ -224,7 +269,7 @@ def evaluate_model(model, val_loader, criterion, writer=None, fold=0):
     correct = torch.zeros((), dtype=torch.long, device=device)
     preds_all, labels_all = [], []
     with torch.no_grad():
-        for inputs, labels in cuda_prefetch(val_loader, device):
+        for inputs, labels in cuda_prefetch(val_loader, device, reuse_buffers=True):
             outputs = model(inputs)
             loss_sum += criterion(outputs, labels).item() * inputs.size(0)
             preds = outputs.argmax(dim=1)
@@ -255,7 +300,7 @@ def evaluate_model_test(model, data_loader, device):
     dataset = data_loader.dataset
     results = HostCollector()
     with torch.no_grad():
-        for batch_idx, (inputs, labels) in enumerate(cuda_prefetch(data_loader, device)):
+        for batch_idx, (inputs, labels) in enumerate(cuda_prefetch(data_loader, device, reuse_buffers=True)):
             embeddings, outputs = model(inputs)
             probs = F.softmax(outputs, dim=1)
             preds = outputs.argmax(dim=1)

@@ -350,3 +350,24 @@ def test_host_collector_keeps_order_with_ragged_batches():
     for i, (a, b) in enumerate(out):
         assert (a == 2.0 * i).all() and (b == np.arange(sizes[i]) + 100 * i).all()
     assert c.finish() == []
+
+
+@pytest.mark.parametrize("reuse", [False, True])
+def test_cuda_prefetch_delivers_every_batch_intact(reuse):
+    """Uploads overlap the consumer's work; with reuse_buffers the two device buffer sets are recycled only after the
+    consumer's stream is done with them (a slow consumer kernel must still see its own batch)."""
+    from heuristique_style_transfer_code_b200.functions import cuda_prefetch
+    sizes = [64, 64, 64, 64, 64, 64, 17]
+    host = [(torch.full((n, 3, 64, 64), float(i)).pin_memory(), torch.full((n,), i, dtype=torch.int64).pin_memory())
+            for i, n in enumerate(sizes)]
+    w = torch.randn(4096, 4096, device="cuda")
+    sums, labels = [], []
+    for x, y in cuda_prefetch(iter(host), "cuda", reuse_buffers=reuse):
+        assert x.is_cuda and y.is_cuda
+        for _ in range(20):                       # keep the stream busy so that the next upload could overtake
+            w = torch.tanh(w @ w * 1e-4)
+        sums.append(x.sum() / x.numel())
+        labels.append(y.float().mean())
+    torch.cuda.synchronize()
+    assert [round(float(s), 4) for s in sums] == [float(i) for i in range(len(sizes))]
+    assert [round(float(s), 4) for s in labels] == [float(i) for i in range(len(sizes))]
