@@ -658,7 +658,8 @@ int gh_patch_gram_fwd(const float* const* maps, const int* H, const int* W, cons
   float* pooled = workspace + planes * 4;                            // (L, B, D, 16)
   const long long gx = (long long)B * ((D + 7) / 8);
   if (gx > 0x7fffffffLL) return GH_ERR_UNSUPPORTED;
-  patch_pool_kernel<<<dim3((unsigned)gx, L), kPatchThreads, 0, (cudaStream_t)stream>>>(p, pooled, stats);
+  patch_pool_kernel<<<dim3((unsigned)gx, L), kPatchThreads, (kPatchThreads / 32) * kPatchSmallPlane * sizeof(float),
+                      (cudaStream_t)stream>>>(p, pooled, stats);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   const size_t smem = (size_t)D * kPatchBins * 4 + 32 * sizeof(double);

@@ -70,6 +70,11 @@ __device__ __forceinline__ void pool_plane_rows(const float* __restrict__ plane,
   const int lane = threadIdx.x & 31;
   unsigned colmask[KMAX];
   float colsum[KMAX];
+  float rowacc[kPatchPool][KMAX];
+#pragma unroll
+  for (int i = 0; i < kPatchPool; ++i)
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) rowacc[i][k] = 0.f;
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) {
     const int x = lane + 32 * k;
@@ -110,18 +115,24 @@ __device__ __forceinline__ void pool_plane_rows(const float* __restrict__ plane,
         }
     }
 #pragma unroll
+    for (int i = 0; i < kPatchPool; ++i)
+      if ((rm >> i) & 1u) {                            // warp-uniform
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) rowacc[i][k] += colsum[k];
+      }
+#pragma unroll
     for (int k = 0; k < KMAX; ++k) {
-      const float c = colsum[k];
-      sum += c;
+      sum += colsum[k];
       colsum[k] = 0.f;
-#pragma unroll
-      for (int i = 0; i < kPatchPool; ++i)
-#pragma unroll
-        for (int j = 0; j < kPatchPool; ++j)
-          acc[i * kPatchPool + j] += (((rm >> i) & 1u) && ((colmask[k] >> j) & 1u)) ? c : 0.f;
     }
     y = yend;
   }
+#pragma unroll
+  for (int i = 0; i < kPatchPool; ++i)
+#pragma unroll
+    for (int j = 0; j < kPatchPool; ++j)
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) acc[i * kPatchPool + j] += ((colmask[k] >> j) & 1u) ? rowacc[i][k] : 0.f;
 }
 
 // Vector path (rows contiguous and 16 B aligned, W % 4 == 0, W <= 4*LPR): LPR lanes cover one row with a float4 each, so one
@@ -197,6 +208,46 @@ __device__ __forceinline__ void pool_plane_vec4(const float* __restrict__ plane,
       for (int e = 0; e < 4; ++e) acc[i * kPatchPool + j] += ((colmask[e] >> j) & 1u) ? rowacc[i][e] : 0.f;
 }
 
+// Small planes (H*W <= kPatchSmallPlane): the walk above costs ~1000 instructions per plane whatever its size. Here
+// the warp copies its plane into shared memory (accumulating sum and sum of squares on the way), then lane i < 16 adds
+// up the (at most (H/4+1) x (W/4+1)) elements of bin i: ~10x fewer instructions for the 14x14 .. 28x28 maps.
+constexpr int kPatchSmallPlane = 1024;
+
+__device__ __forceinline__ float pool_plane_small(const float* __restrict__ plane, int H, int W, long long s_y,
+                                                  long long s_x, float* buf, float& sum, float& sq) {
+  const int lane = threadIdx.x & 31;
+  const int n = H * W;
+  if (s_x == 1 && s_y == W) {
+    for (int i = lane; i < n; i += 32) {
+      const float v = __ldg(plane + i);
+      buf[i] = v;
+      sum += v;
+      sq = fmaf(v, v, sq);
+    }
+  } else {
+    for (int i = lane; i < n; i += 32) {
+      const int y = i / W, x = i - y * W;
+      const float v = __ldg(plane + (long long)y * s_y + (long long)x * s_x);
+      buf[i] = v;
+      sum += v;
+      sq = fmaf(v, v, sq);
+    }
+  }
+  __syncwarp();
+  float mean = 0.f;
+  if (lane < kPatchBins) {
+    const int by = lane / kPatchPool, bx = lane % kPatchPool;
+    const int y0 = (by * H) / kPatchPool, y1 = ((by + 1) * H + kPatchPool - 1) / kPatchPool;
+    const int x0 = (bx * W) / kPatchPool, x1 = ((bx + 1) * W + kPatchPool - 1) / kPatchPool;
+    float s = 0.f;
+    for (int y = y0; y < y1; ++y)
+      for (int x = x0; x < x1; ++x) s += buf[y * W + x];
+    mean = s / (float)((y1 - y0) * (x1 - x0));
+  }
+  __syncwarp();
+  return mean;
+}
+
 // Any strides / any width: lanes along x, every element tested against the four column bins.
 __device__ __forceinline__ void pool_plane_generic(const float* __restrict__ plane, int H, int W, long long s_y,
                                                    long long s_x, const int* ys, const int* ye, const int* xs,
@@ -239,6 +290,19 @@ __global__ void __launch_bounds__(kPatchThreads, 3) patch_pool_kernel(const Patc
     xs[i] = (i * W) / kPatchPool;  xe[i] = ((i + 1) * W + kPatchPool - 1) / kPatchPool;
   }
   const float* plane = ly.x + (long long)b * ly.s_img + (long long)c * ly.s_c;
+  const long long plane_id = ((long long)l * p.B + b) * D + c;
+  if (H * W <= kPatchSmallPlane) {                    // uniform over the CTA (one layer per blockIdx.y)
+    extern __shared__ float small_planes[];
+    float sum = 0.f, sq = 0.f;
+    const float mean = pool_plane_small(plane, H, W, ly.s_y, ly.s_x, small_planes + warp * kPatchSmallPlane, sum, sq);
+    if (lane < kPatchBins) pooled[plane_id * kPatchBins + lane] = mean;
+    const float fsum = warp_sum(sum), fsq = warp_sum(sq);
+    if (lane == 0) {
+      stats[plane_id * 2] = (double)fsum;
+      stats[plane_id * 2 + 1] = (double)fsq;
+    }
+    return;
+  }
   float acc[kPatchBins];
 #pragma unroll
   for (int i = 0; i < kPatchBins; ++i) acc[i] = 0.f;
@@ -246,15 +310,14 @@ __global__ void __launch_bounds__(kPatchThreads, 3) patch_pool_kernel(const Patc
   const bool vec = ly.s_x == 1 && (W & 3) == 0 && (ly.s_y & 3) == 0 && (ly.s_c & 3) == 0 && (ly.s_img & 3) == 0 &&
                    (reinterpret_cast<uintptr_t>(ly.x) & 15) == 0;
   if (vec && W <= 32) pool_plane_vec4<8, 4>(plane, H, W, ly.s_y, ys, ye, xs, xe, acc, sum, sq);
-  else if (vec && W <= 64) pool_plane_vec4<16, 4>(plane, H, W, ly.s_y, ys, ye, xs, xe, acc, sum, sq);
-  else if (vec && W <= 128) pool_plane_vec4<32, 8>(plane, H, W, ly.s_y, ys, ye, xs, xe, acc, sum, sq);
+  else if (vec && W <= 64) pool_plane_vec4<16, 7>(plane, H, W, ly.s_y, ys, ye, xs, xe, acc, sum, sq);
+  else if (vec && W <= 128) pool_plane_vec4<32, 7>(plane, H, W, ly.s_y, ys, ye, xs, xe, acc, sum, sq);
   else if (ly.s_x == 1 && W <= 32) pool_plane_rows<1>(plane, H, W, ly.s_y, ys, ye, xs, xe, acc, sum, sq);
   else if (ly.s_x == 1 && W <= 64) pool_plane_rows<2>(plane, H, W, ly.s_y, ys, ye, xs, xe, acc, sum, sq);
   else if (ly.s_x == 1 && W <= 128) pool_plane_rows<4>(plane, H, W, ly.s_y, ys, ye, xs, xe, acc, sum, sq);
   else if (ly.s_x == 1 && W <= 256) pool_plane_rows<8>(plane, H, W, ly.s_y, ys, ye, xs, xe, acc, sum, sq);
   else pool_plane_generic(plane, H, W, ly.s_y, ly.s_x, ys, ye, xs, xe, acc, sum, sq);
 
-  const long long plane_id = ((long long)l * p.B + b) * D + c;
   // halving butterfly: 16 values per lane -> lane (i << 1) holds bin i summed over the warp (16 shuffles instead of 80)
 #pragma unroll
   for (int half = 8, o = 16; half >= 1; half >>= 1, o >>= 1) {
