@@ -12,6 +12,7 @@
 #include "preprocess.cuh"
 #include "transpose.cuh"
 #include "patchgan.cuh"
+#include "pool.cuh"
 #include <string>
 
 namespace gh {
@@ -627,6 +628,27 @@ int gh_gemm_f32(const float* A, long long a_sm, long long a_sk, const float* Bm,
                 const float* bias, float* D, long long ldd, int M, int N, int K, void* stream) {
   if (!A || !Bm || !D || M <= 0 || N <= 0 || K <= 0) return GH_ERR_BAD_ARG;
   return (int)gemm_auto(A, a_sm, a_sk, Bm, b_sk, b_sn, bias, D, ldd, M, N, K, 0, (cudaStream_t)stream);
+}
+
+int gh_maxpool2d_nhwc(const void* in, int dtype, void* out, int B, int H, int W, int C, int k, int stride, int pad,
+                      void* stream) {
+  if (!in || !out || B <= 0 || H <= 0 || W <= 0 || C <= 0 || k <= 0 || stride <= 0 || pad < 0) return GH_ERR_BAD_ARG;
+  if (dtype != GH_DTYPE_F32 && dtype != GH_DTYPE_BF16) return GH_ERR_BAD_ARG;
+  if (2 * pad > k) return GH_ERR_BAD_ARG;                       // torch's own constraint: pad <= k / 2
+  const int vec = dtype == GH_DTYPE_F32 ? 4 : 8;
+  if (C % vec != 0 || (uintptr_t)in % 16 != 0 || (uintptr_t)out % 16 != 0) return GH_ERR_UNSUPPORTED;
+  MaxPoolParams p{};
+  p.in = in; p.out = out; p.B = B; p.H = H; p.W = W; p.C = C; p.k = k; p.stride = stride; p.pad = pad;
+  p.OH = (H + 2 * pad - k) / stride + 1;                         // floor mode (ceil_mode=False), dilation 1
+  p.OW = (W + 2 * pad - k) / stride + 1;
+  if (p.OH <= 0 || p.OW <= 0) return GH_ERR_BAD_ARG;
+  p.total_vec = (long long)B * p.OH * p.OW * (C / vec);
+  const long long want = (p.total_vec + 255) / 256;
+  const long long cap = (long long)gh_sm_count() * 32;
+  const int grid = (int)(want < cap ? want : cap);
+  if (dtype == GH_DTYPE_F32) maxpool2d_nhwc_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  else maxpool2d_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  return (int)cudaGetLastError();
 }
 
 long long gh_patch_gram_workspace(int L, int B, int D) {

@@ -15,11 +15,18 @@ knows (stem + Bottleneck stages); anything else runs the children one by one as 
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Tuple
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+from . import ops
+
+# Stem input channels are zero-padded to this count (weights too) when > 3: cuDNN has no good NHWC kernel for a
+# 3-channel 7x7 convolution (it runs an sm80 implicit-GEMM without shared memory, 15 % of the folded encoder).
+STEM_CHANNELS = int(os.environ.get("GRAMHEAD_STEM_CHANNELS", "3"))
 
 
 def _fold(conv: nn.Conv2d, bn: nn.BatchNorm2d, dtype: torch.dtype, channels_last: bool):
@@ -84,13 +91,27 @@ class FoldedEncoder:
             return None
         with torch.no_grad():
             stem = _fold(encoder[0], encoder[1], dtype, channels_last)
+            if STEM_CHANNELS > stem[0].shape[1] and channels_last:
+                w = stem[0]
+                wp = w.new_zeros((w.shape[0], STEM_CHANNELS, w.shape[2], w.shape[3]))
+                wp[:, :w.shape[1]] = w
+                stem = (wp.contiguous(memory_format=torch.channels_last),) + tuple(stem[1:])
             stages: List[list] = []
             for stage in list(encoder)[4:]:
                 blocks = []
                 for b in stage:
-                    down = _fold(b.downsample[0], b.downsample[1], dtype, channels_last) if b.downsample is not None else None
+                    c3 = _fold(b.conv3, b.bn3, dtype, channels_last)
+                    down = None
+                    if b.downsample is not None:
+                        # relu(conv3(y) + b3 + conv_d(x) + b_d): both biases go into the fused epilogue of conv3, so the
+                        # shortcut convolution needs no bias pass over its (B, 4*planes, H, W) output
+                        dw, db, *geom = _fold(b.downsample[0], b.downsample[1], torch.float32, channels_last)
+                        bias3 = (c3[1].float() + db).to(dtype)
+                        c3 = (c3[0], bias3) + tuple(c3[2:])
+                        down = (dw.to(dtype).contiguous(memory_format=torch.channels_last if channels_last
+                                                        else torch.contiguous_format), None) + tuple(geom)
                     blocks.append((_fold(b.conv1, b.bn1, dtype, channels_last), _fold(b.conv2, b.bn2, dtype, channels_last),
-                                   _fold(b.conv3, b.bn3, dtype, channels_last), down))
+                                   c3, down))
                 stages.append(blocks)
         return cls(stem, encoder[3], stages, encoder_signature(encoder), dtype, channels_last)
 
@@ -99,12 +120,29 @@ class FoldedEncoder:
         w, b, stride, padding, dilation, groups = p
         return torch.cudnn_convolution_relu(x, w, b, stride, padding, dilation, groups)
 
+    def _pool(self, x):
+        p = self.pool
+        k, s, pad = p.kernel_size, p.stride, p.padding
+        plain = (isinstance(k, int) and isinstance(s, int) and isinstance(pad, int) and p.dilation == 1
+                 and not p.ceil_mode and not p.return_indices)
+        vec = 4 if x.dtype == torch.float32 else 8
+        if plain and self.channels_last and x.shape[1] % vec == 0 and x.is_contiguous(memory_format=torch.channels_last):
+            return ops.maxpool2d_nhwc(x, k, s, pad)
+        return p(x)
+
     def __call__(self, x: torch.Tensor):
-        x = x.to(self.dtype)
-        if self.channels_last:
-            x = x.contiguous(memory_format=torch.channels_last)
+        cin = self.stem[0].shape[1]
+        if cin > x.shape[1]:                    # padded stem: one strided copy instead of the channels_last conversion
+            xp = torch.empty((x.shape[0], cin, x.shape[2], x.shape[3]), device=x.device, dtype=self.dtype,
+                             memory_format=torch.channels_last).zero_()
+            xp[:, :x.shape[1]] = x
+            x = xp
+        else:
+            x = x.to(self.dtype)
+            if self.channels_last:
+                x = x.contiguous(memory_format=torch.channels_last)
         x = self._conv_relu(x, self.stem)
-        x = self.pool(x)
+        x = self._pool(x)
         outs = []
         for blocks in self.stages:
             for c1, c2, c3, down in blocks:

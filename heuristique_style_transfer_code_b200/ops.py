@@ -242,6 +242,23 @@ def gemm_f32(a: torch.Tensor, b: torch.Tensor, bias: torch.Tensor = None) -> tor
     return out
 
 
+def maxpool2d_nhwc(x: torch.Tensor, kernel: int, stride: int, padding: int) -> torch.Tensor:
+    """nn.MaxPool2d(kernel, stride, padding) (floor mode, dilation 1) of a channels_last (B, C, H, W) fp32 / bf16
+    activation, values only (gh_maxpool2d_nhwc); the result is channels_last again."""
+    _require_cuda(x, "x")
+    if x.dim() != 4 or not x.is_contiguous(memory_format=torch.channels_last):
+        raise GramHeadError("gramhead: maxpool2d_nhwc takes a channels_last (B, C, H, W) tensor")
+    b, c, h, w = x.shape
+    oh, ow = (h + 2 * padding - kernel) // stride + 1, (w + 2 * padding - kernel) // stride + 1
+    out = torch.empty((b, c, oh, ow), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+    work = dict(bytes=(x.numel() + out.numel()) * x.element_size(), flops=0, kind="maxpool")
+    with torch.cuda.device(x.device), _Timed(f"maxpool2d_nhwc[C={c},HW={h}x{w},{x.dtype}]", 1, x.device, **work):
+        rc = _lib.lib().gh_maxpool2d_nhwc(x.data_ptr(), _dtype_code(x), out.data_ptr(), b, h, w, c, kernel, stride, padding,
+                                          _stream_ptr(x))
+    check(rc, "gh_maxpool2d_nhwc")
+    return out
+
+
 def patch_gram(maps: Sequence[torch.Tensor], ln_input: bool = True):
     """The L collected (B, D, H_l, W_l) fp32 maps of one Multi-PatchGAN discriminator -> (gram (L, B, D*D),
     gram_norm (L, B)) through gh_patch_gram_fwd: [layer norm over the map,] 4x4 adaptive average pooling, layer norm,

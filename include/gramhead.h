@@ -131,6 +131,15 @@ int gh_preprocess_frame(const unsigned char* frame, long long pitch_bytes, int H
 int gh_gemm_f32(const float* A, long long a_sm, long long a_sk, const float* B, long long b_sk, long long b_sn,
                 const float* bias, float* D, long long ldd, int M, int N, int K, void* stream);
 
+/* Max pooling of a channels_last activation, values only (inference plan of the encoder, frozen_encoder.py). Replaces the
+ * nn.MaxPool2d child of the truncated encoder (torchvision resnet `maxpool`: kernel 3, stride 2, padding 1; child 3 of
+ * `self.truncated_encoder`, Models/Models_RESNET50_TRUNCATE_GRAM_with_Attention.py:17,40) under eval + no_grad, where
+ * the argmax indices ATen's kernel also produces are not needed. in: (B, H, W, C) dense NHWC storage of a (B, C, H, W)
+ * channels_last tensor, fp32 or bf16; out: (B, OH, OW, C) with OH = (H + 2*pad - k)/stride + 1 (floor mode, dilation 1).
+ * NaN-propagating like ATen; bit-identical results. C % 4 == 0 (fp32) / C % 8 == 0 (bf16), 16 B aligned pointers. */
+int gh_maxpool2d_nhwc(const void* in, int dtype, void* out, int B, int H, int W, int C, int k, int stride, int pad,
+                      void* stream);
+
 /* ---- Gram head of the Multi-PatchGAN discriminator (the *_test classes of Models/Models_Multi_PatchGAN.py) ----------
  * gh_patch_gram_fwd replaces, for all L collected feature maps of one discriminator in one launch,
  *   F.layer_norm(x_proj, x_proj.shape[1:])                  :198   (only when ln_input != 0; otherwise pass the

@@ -371,3 +371,19 @@ def test_cuda_prefetch_delivers_every_batch_intact(reuse):
     torch.cuda.synchronize()
     assert [round(float(s), 4) for s in sums] == [float(i) for i in range(len(sizes))]
     assert [round(float(s), 4) for s in labels] == [float(i) for i in range(len(sizes))]
+
+
+@pytest.mark.parametrize("shape,k,s,p", [((4, 64, 112, 112), 3, 2, 1), ((2, 64, 57, 33), 3, 2, 1), ((3, 16, 9, 9), 2, 2, 0),
+                                         ((2, 8, 7, 12), 3, 1, 1)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_maxpool_nhwc_is_bit_identical_to_aten(shape, k, s, p, dtype):
+    from heuristique_style_transfer_code_b200 import ops
+    torch.manual_seed(sum(shape))
+    x = torch.randn(shape, device="cuda").to(dtype).contiguous(memory_format=torch.channels_last)
+    x[0, 1, 2, 3] = float("nan")                                   # ATen propagates NaN through the window
+    x[-1, 0, 0, 0] = float("-inf")
+    got = ops.maxpool2d_nhwc(x, k, s, p)
+    want = torch.nn.functional.max_pool2d(x, k, s, p)
+    assert got.shape == want.shape and got.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(torch.isnan(got), torch.isnan(want))
+    assert torch.equal(torch.nan_to_num(got.float(), nan=0.0), torch.nan_to_num(want.float(), nan=0.0))
