@@ -643,11 +643,30 @@ int gh_maxpool2d_nhwc(const void* in, int dtype, void* out, int B, int H, int W,
   p.OW = (W + 2 * pad - k) / stride + 1;
   if (p.OH <= 0 || p.OW <= 0) return GH_ERR_BAD_ARG;
   p.total_vec = (long long)B * p.OH * p.OW * (C / vec);
-  const long long want = (p.total_vec + 255) / 256;
-  const long long cap = (long long)gh_sm_count() * 32;
-  const int grid = (int)(want < cap ? want : cap);
+  const int cv = C / vec;
+  if (cv > 256 || B > 65535) return GH_ERR_UNSUPPORTED;
+  const int ppc = 256 / cv;
+  const dim3 grid((p.OW + ppc - 1) / ppc, (p.OH + kPoolRows - 1) / kPoolRows, B);
+  if (grid.y > 65535) return GH_ERR_UNSUPPORTED;
   if (dtype == GH_DTYPE_F32) maxpool2d_nhwc_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
   else maxpool2d_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  return (int)cudaGetLastError();
+}
+
+int gh_stem_space_to_depth(const float* x, long long img_stride, long long c_stride, long long y_stride,
+                           long long x_stride, int B, int H, int W, void* z, int z_dtype, void* stream) {
+  if (!x || !z || B <= 0 || H <= 0 || W <= 0) return GH_ERR_BAD_ARG;
+  if (z_dtype != GH_DTYPE_F32 && z_dtype != GH_DTYPE_BF16) return GH_ERR_BAD_ARG;
+  if ((H & 1) || (W & 1) || (uintptr_t)z % 16 != 0) return GH_ERR_UNSUPPORTED;
+  StemS2DParams p{};
+  p.x = x; p.z = z; p.s_img = img_stride; p.s_c = c_stride; p.s_y = y_stride; p.s_x = x_stride;
+  p.B = B; p.H = H; p.W = W; p.HP = H / 2 + 3; p.WP = W / 2 + 3;
+  p.total = (long long)B * p.HP * p.WP;
+  const long long want = (p.total + 255) / 256;
+  const long long cap = (long long)gh_sm_count() * 32;
+  const int grid = (int)(want < cap ? want : cap);
+  if (z_dtype == GH_DTYPE_F32) stem_space_to_depth_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  else stem_space_to_depth_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
   return (int)cudaGetLastError();
 }
 

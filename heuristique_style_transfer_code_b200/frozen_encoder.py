@@ -24,9 +24,23 @@ import torch.nn.functional as F
 
 from . import ops
 
-# Stem input channels are zero-padded to this count (weights too) when > 3: cuDNN has no good NHWC kernel for a
-# 3-channel 7x7 convolution (it runs an sm80 implicit-GEMM without shared memory, 15 % of the folded encoder).
-STEM_CHANNELS = int(os.environ.get("GRAMHEAD_STEM_CHANNELS", "3"))
+# cuDNN has no good NHWC kernel for the stem's 3-channel 7x7 stride-2 convolution (an sm80 implicit GEMM without shared
+# memory: 1.33 ms of a 7.0 ms step at batch 256). The same convolution over the 2x2 space-to-depth image -- 4x4, stride
+# 1, 12 channels padded to 16 -- runs on its regular tensor-core kernels in 0.58 ms (tools/time_stem.py; identical sums
+# in another order: 3e-6). GRAMHEAD_STEM_S2D=0 keeps the direct convolution.
+STEM_SPACE_TO_DEPTH = os.environ.get("GRAMHEAD_STEM_S2D", "1") != "0"
+
+
+def _stem_space_to_depth_weight(weight: torch.Tensor) -> torch.Tensor:
+    """(O, 3, 7, 7) -> (O, 16, 4, 4), channels_last: tap i' = i + 1 = 2a + r of an 8x8 kernel whose first row and column
+    are zero goes to tap a of channel c*4 + r*2 + s (see gh_stem_space_to_depth)."""
+    o = weight.shape[0]
+    w8 = weight.new_zeros((o, 3, 8, 8))
+    w8[:, :, 1:, 1:] = weight
+    w12 = w8.view(o, 3, 4, 2, 4, 2).permute(0, 1, 3, 5, 2, 4).reshape(o, 12, 4, 4)
+    w16 = weight.new_zeros((o, 16, 4, 4))
+    w16[:, :12] = w12
+    return w16.contiguous(memory_format=torch.channels_last)
 
 
 def _fold(conv: nn.Conv2d, bn: nn.BatchNorm2d, dtype: torch.dtype, channels_last: bool):
@@ -72,6 +86,7 @@ class FoldedEncoder:
 
     def __init__(self, stem, pool, stages, signature, dtype, channels_last):
         self.stem, self.pool, self.stages = stem, pool, stages
+        self.stem_s2d = None
         self.signature, self.dtype, self.channels_last = signature, dtype, channels_last
 
     @staticmethod
@@ -91,11 +106,11 @@ class FoldedEncoder:
             return None
         with torch.no_grad():
             stem = _fold(encoder[0], encoder[1], dtype, channels_last)
-            if STEM_CHANNELS > stem[0].shape[1] and channels_last:
-                w = stem[0]
-                wp = w.new_zeros((w.shape[0], STEM_CHANNELS, w.shape[2], w.shape[3]))
-                wp[:, :w.shape[1]] = w
-                stem = (wp.contiguous(memory_format=torch.channels_last),) + tuple(stem[1:])
+            conv1 = encoder[0]
+            stem_s2d = None
+            if (STEM_SPACE_TO_DEPTH and channels_last and conv1.in_channels == 3 and conv1.kernel_size == (7, 7)
+                    and conv1.stride == (2, 2) and conv1.padding == (3, 3) and conv1.dilation == (1, 1) and conv1.groups == 1):
+                stem_s2d = (_stem_space_to_depth_weight(stem[0].float()).to(dtype), stem[1], (1, 1), (0, 0), (1, 1), 1)
             stages: List[list] = []
             for stage in list(encoder)[4:]:
                 blocks = []
@@ -113,7 +128,9 @@ class FoldedEncoder:
                     blocks.append((_fold(b.conv1, b.bn1, dtype, channels_last), _fold(b.conv2, b.bn2, dtype, channels_last),
                                    c3, down))
                 stages.append(blocks)
-        return cls(stem, encoder[3], stages, encoder_signature(encoder), dtype, channels_last)
+        plan = cls(stem, encoder[3], stages, encoder_signature(encoder), dtype, channels_last)
+        plan.stem_s2d = stem_s2d
+        return plan
 
     @staticmethod
     def _conv_relu(x, p):
@@ -131,17 +148,14 @@ class FoldedEncoder:
         return p(x)
 
     def __call__(self, x: torch.Tensor):
-        cin = self.stem[0].shape[1]
-        if cin > x.shape[1]:                    # padded stem: one strided copy instead of the channels_last conversion
-            xp = torch.empty((x.shape[0], cin, x.shape[2], x.shape[3]), device=x.device, dtype=self.dtype,
-                             memory_format=torch.channels_last).zero_()
-            xp[:, :x.shape[1]] = x
-            x = xp
+        if (self.stem_s2d is not None and x.dtype == torch.float32 and x.shape[1] == 3 and x.shape[2] % 2 == 0
+                and x.shape[3] % 2 == 0):
+            x = self._conv_relu(ops.stem_space_to_depth(x, self.dtype), self.stem_s2d)
         else:
             x = x.to(self.dtype)
             if self.channels_last:
                 x = x.contiguous(memory_format=torch.channels_last)
-        x = self._conv_relu(x, self.stem)
+            x = self._conv_relu(x, self.stem)
         x = self._pool(x)
         outs = []
         for blocks in self.stages:

@@ -259,6 +259,22 @@ def maxpool2d_nhwc(x: torch.Tensor, kernel: int, stride: int, padding: int) -> t
     return out
 
 
+def stem_space_to_depth(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """(B, 3, H, W) fp32 images (any strides) -> channels_last (B, 16, H/2 + 3, W/2 + 3) in `dtype`: the zero-bordered
+    2x2 space-to-depth image over which the stem's 7x7 stride-2 convolution is a 4x4 stride-1 one (gh_stem_space_to_depth)."""
+    _require_cuda(x, "x")
+    if x.dim() != 4 or x.shape[1] != 3 or x.dtype != torch.float32 or x.shape[2] % 2 or x.shape[3] % 2:
+        raise GramHeadError("gramhead: stem_space_to_depth takes fp32 (B, 3, H, W) images with even H and W")
+    b, _, h, w = x.shape
+    z = torch.empty((b, 16, h // 2 + 3, w // 2 + 3), device=x.device, dtype=dtype, memory_format=torch.channels_last)
+    work = dict(bytes=x.numel() * 4 + z.numel() * z.element_size(), flops=0, kind="stem_s2d")
+    with torch.cuda.device(x.device), _Timed(f"stem_space_to_depth[HW={h}x{w},{dtype}]", 1, x.device, **work):
+        rc = _lib.lib().gh_stem_space_to_depth(x.data_ptr(), x.stride(0), x.stride(1), x.stride(2), x.stride(3), b, h, w,
+                                               z.data_ptr(), _dtype_code(z), _stream_ptr(x))
+    check(rc, "gh_stem_space_to_depth")
+    return z
+
+
 def patch_gram(maps: Sequence[torch.Tensor], ln_input: bool = True):
     """The L collected (B, D, H_l, W_l) fp32 maps of one Multi-PatchGAN discriminator -> (gram (L, B, D*D),
     gram_norm (L, B)) through gh_patch_gram_fwd: [layer norm over the map,] 4x4 adaptive average pooling, layer norm,

@@ -140,6 +140,16 @@ int gh_gemm_f32(const float* A, long long a_sm, long long a_sk, const float* B, 
 int gh_maxpool2d_nhwc(const void* in, int dtype, void* out, int B, int H, int W, int C, int k, int stride, int pad,
                       void* stream);
 
+/* Space-to-depth staging of the image batch for the stem convolution of the inference plan (frozen_encoder.py): the
+ * stem `conv1` (7x7, stride 2, padding 3, 3 input channels; child 0 of `self.truncated_encoder`,
+ * Models/Models_RESNET50_TRUNCATE_GRAM_with_Attention.py:17,37) is evaluated by cuDNN as the equivalent 4x4 stride-1
+ * convolution over z, which this call builds in place of the NCHW -> channels_last conversion of the input:
+ *   z[b, Y + 2, X + 2, c*4 + r*2 + s] = x[b, c, 2Y + r, 2X + s],  zero elsewhere,
+ * z: dense NHWC storage of a (B, 16, H/2 + 3, W/2 + 3) channels_last tensor, fp32 or bf16 (z_dtype); x: fp32 with the
+ * given element strides (NCHW or channels_last). H and W even (GH_ERR_UNSUPPORTED otherwise). */
+int gh_stem_space_to_depth(const float* x, long long img_stride, long long c_stride, long long y_stride,
+                           long long x_stride, int B, int H, int W, void* z, int z_dtype, void* stream);
+
 /* ---- Gram head of the Multi-PatchGAN discriminator (the *_test classes of Models/Models_Multi_PatchGAN.py) ----------
  * gh_patch_gram_fwd replaces, for all L collected feature maps of one discriminator in one launch,
  *   F.layer_norm(x_proj, x_proj.shape[1:])                  :198   (only when ln_input != 0; otherwise pass the

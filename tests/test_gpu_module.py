@@ -387,3 +387,39 @@ def test_maxpool_nhwc_is_bit_identical_to_aten(shape, k, s, p, dtype):
     assert got.shape == want.shape and got.is_contiguous(memory_format=torch.channels_last)
     assert torch.equal(torch.isnan(got), torch.isnan(want))
     assert torch.equal(torch.nan_to_num(got.float(), nan=0.0), torch.nan_to_num(want.float(), nan=0.0))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("layout", ["nchw", "channels_last", "strided"])
+def test_stem_space_to_depth_staging(dtype, layout):
+    from heuristique_style_transfer_code_b200 import ops
+    torch.manual_seed(3)
+    b, h, w = 3, 36, 52
+    x = torch.randn(b, 3, h, w, device="cuda")
+    if layout == "channels_last":
+        x = x.contiguous(memory_format=torch.channels_last)
+    elif layout == "strided":
+        big = torch.randn(b, 3, h + 2, w + 3, device="cuda")
+        big[:, :, 1:h + 1, 1:w + 1] = x
+        x = big[:, :, 1:h + 1, 1:w + 1]                      # odd offsets: the scalar-load path
+    z = ops.stem_space_to_depth(x, dtype)
+    want = torch.zeros(b, 16, h // 2 + 3, w // 2 + 3, device="cuda")
+    want[:, :12, 2:h // 2 + 2, 2:w // 2 + 2] = x.reshape(b, 3, h // 2, 2, w // 2, 2).permute(0, 1, 3, 5, 2, 4).reshape(b, 12, h // 2, w // 2)
+    assert z.shape == want.shape and z.dtype == dtype and z.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(z, want.to(dtype))
+
+
+def test_inference_plan_on_odd_image_sizes_uses_the_direct_stem():
+    from torchvision import models
+    from heuristique_style_transfer_code_b200 import TruncatedResNet50_for_test
+    torch.manual_seed(0)
+    m = TruncatedResNet50_for_test(models.resnet50(weights=None), 6, 4, 32, device="cuda").eval()
+    _randomise_batchnorm(m)
+    for size in ((225, 225), (224, 192)):
+        x = torch.randn(4, 3, *size, device="cuda")
+        with torch.no_grad():
+            m.fold_batchnorm = True
+            e1, l1 = m(x)
+            m.fold_batchnorm = False
+            e0, l0 = m(x)
+        assert O.rel_err(npf(e1), npf(e0)) <= 2e-5 and O.rel_err(npf(l1), npf(l0)) <= 2e-5

@@ -52,3 +52,32 @@ for dtype in (torch.float32, torch.bfloat16):
     print(f"{dtype} max pool: ATen {timed(lambda: torch.nn.functional.max_pool2d(y, 3, 2, 1)):8.1f} us   "
           f"gh_maxpool2d_nhwc {timed(lambda: ops.maxpool2d_nhwc(y, 3, 2, 1)):8.1f} us   "
           f"roofline {(y.numel() * 1.25 * y.element_size()) / 6548.8e3:6.1f} us", flush=True)
+
+# ---- space-to-depth formulation: 7x7 stride-2 conv on 3 channels == 4x4 stride-1 conv on 12 channels ----
+for dtype in (torch.float32, torch.bfloat16):
+    x = x3.to(dtype)
+    w = w3.to(dtype)
+    b = bias.to(dtype)
+    direct = torch.cudnn_convolution_relu(x.contiguous(memory_format=torch.channels_last),
+                                          w.contiguous(memory_format=torch.channels_last), b, (2, 2), (3, 3), (1, 1), 1)
+    w8 = torch.zeros(64, 3, 8, 8, device="cuda", dtype=dtype)
+    w8[:, :, 1:, 1:] = w                                   # tap i' = i + 1, i' = 2a + r
+    ws = w8.view(64, 3, 4, 2, 4, 2).permute(0, 1, 3, 5, 2, 4).reshape(64, 12, 4, 4).contiguous(memory_format=torch.channels_last)
+    # input coordinate 2y + i' - 4 = 2(y + a - 2) + r: z[(c,r,s), Y, X] = in[c, 2Y + r, 2X + s], taps Y = y + a - 2
+    z = torch.empty(B, 12, 112 + 3, 112 + 3, device="cuda", dtype=dtype, memory_format=torch.channels_last).zero_()
+    zz = x.view(B, 3, 112, 2, 112, 2).permute(0, 1, 3, 5, 2, 4).reshape(B, 12, 112, 112)
+    z[:, :, 2:114, 2:114] = zz
+    f = lambda: torch.cudnn_convolution_relu(z, ws, b, (1, 1), (0, 0), (1, 1), 1)
+    y = f()
+    print(f"{dtype} space-to-depth 4x4x12: conv+bias+relu {timed(f):8.1f} us  out {tuple(y.shape)}  "
+          f"rel diff vs direct {float((y.float() - direct.float()).norm() / direct.float().norm()):.2e}", flush=True)
+    for cpad in (16,):
+        zp = torch.empty(B, cpad, 115, 115, device="cuda", dtype=dtype, memory_format=torch.channels_last).zero_()
+        zp[:, :12] = z
+        wp = torch.zeros(64, cpad, 4, 4, device="cuda", dtype=dtype)
+        wp[:, :12] = ws
+        wp = wp.contiguous(memory_format=torch.channels_last)
+        g = lambda: torch.cudnn_convolution_relu(zp, wp, b, (1, 1), (0, 0), (1, 1), 1)
+        y2 = g()
+        print(f"{dtype} space-to-depth 4x4x{cpad}: conv+bias+relu {timed(g):8.1f} us  "
+              f"rel diff vs direct {float((y2.float() - direct.float()).norm() / direct.float().norm()):.2e}", flush=True)
