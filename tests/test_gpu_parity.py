@@ -60,14 +60,30 @@ class kernel_path:
         return False
 
 
-def operand_model_err(got, ref_fn, xf, path, dtype):
+_ORACLE_CACHE = {}
+
+
+def cached_oracle(key, fn):
+    """The three kernel families of one parametrisation see the same seeded input: evaluate the fp64 oracle once."""
+    if key not in _ORACLE_CACHE:
+        if len(_ORACLE_CACHE) > 200:
+            _ORACLE_CACHE.clear()
+        _ORACLE_CACHE[key] = fn()
+    return _ORACLE_CACHE[key]
+
+
+def operand_model_err(got, ref_fn, xf, path, dtype, key=None):
     """Error of `got` against the fp64 oracle fed the operand model of the kernel family that ran.
     ref_fn(rounded_features) -> reference. bf16 features are exact in every family."""
+    def ref(model):
+        if key is None:
+            return ref_fn(model(xf) if model else xf)
+        return cached_oracle(key + (model.__name__ if model else "exact",), lambda: ref_fn(model(xf) if model else xf))
     if dtype == "bf16":
-        return O.rel_err(got, ref_fn(xf))
+        return O.rel_err(got, ref(None))
     models = {"ldg": (O.bf16_round,), "pair": (O.tf32_round, O.bf16_round), "auto": (O.tf32_round, O.bf16_round)}[path]
     # "pair" falls back to the ldg kernels where TMA cannot describe the tensor (e.g. HW = 49: 196 B pitch)
-    return min(O.rel_err(got, ref_fn(m(xf))) for m in models)
+    return min(O.rel_err(got, ref(m)) for m in models)
 
 
 def test_cuda_is_present():
@@ -110,8 +126,9 @@ def test_pooled_gram_forward(ops, B, C, HW, g, ksplit, dtype, path):
     got = npf(desc[:, 1])
     xf = npf(x)
     assert torch.isnan(desc[:, 0]).all(), "the other stage's slice must not be touched"
-    assert O.rel_err(got, O.descriptors([xf], g)[:, 0]) <= 1e-3
-    assert operand_model_err(got, lambda f: O.descriptors([f], g)[:, 0], xf, path, dtype) <= 1e-5
+    key = ("pool_fwd", B, C, HW, g, dtype)
+    assert O.rel_err(got, cached_oracle(key + ("exact",), lambda: O.descriptors([xf], g)[:, 0])) <= 1e-3
+    assert operand_model_err(got, lambda f: O.descriptors([f], g)[:, 0], xf, path, dtype, key) <= 1e-5
     sym = got.reshape(B, g, g)
     assert np.abs(sym - sym.transpose(0, 2, 1)).max() <= 1e-5 * np.abs(sym).max()
 
