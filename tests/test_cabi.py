@@ -52,6 +52,22 @@ def test_argument_validation_without_gpu(library):
     assert library.gh_set_option(b"no_such_option", 1) == _lib.GH_ERR_BAD_ARG
     assert library.gh_set_option(b"gram_fwd_producer_warps", 12) == _lib.GH_ERR_BAD_ARG
     assert library.gh_attn_head_bwd_workspace(4, 3, 64) == 2 * 4 * 64 + 3 * 4 * 3 * 64
+    # Multi-PatchGAN head and inference-plan entries
+    assert library.gh_patch_gram_workspace(6, 256, 64) == 6 * 256 * 64 * 20
+    assert library.gh_patch_gram_fwd(None, None, None, None, 1, 1, 64, 1, None, None, None, None) == _lib.GH_ERR_BAD_ARG
+    ptrs = (ctypes.c_void_p * 9)(*([16] * 9))
+    hw = (ctypes.c_int * 9)(*([4] * 9))
+    st = (ctypes.c_longlong * 36)(*([1] * 36))
+    assert library.gh_patch_gram_fwd(ptrs, hw, hw, st, 9, 1, 64, 1, dummy, dummy, dummy, None) == _lib.GH_ERR_UNSUPPORTED   # > 8 layers
+    assert library.gh_patch_gram_fwd(ptrs, hw, hw, st, 2, 1, 160, 1, dummy, dummy, dummy, None) == _lib.GH_ERR_UNSUPPORTED  # D > 128
+    assert library.gh_patch_attn_fwd(*([None] * 11), 4, 2, 64, 8, 3, None, None, None) == _lib.GH_ERR_BAD_ARG
+    assert library.gh_patch_attn_fwd(*([dummy] * 11), 4, 2, 60, 8, 3, dummy, dummy, None) == _lib.GH_ERR_BAD_ARG            # E % heads
+    assert library.gh_patch_attn_fwd(*([dummy] * 11), 4, 2, 256, 8, 3, dummy, dummy, None) == _lib.GH_ERR_UNSUPPORTED       # E > 128
+    assert library.gh_maxpool2d_nhwc(None, 0, None, 1, 8, 8, 64, 3, 2, 1, None) == _lib.GH_ERR_BAD_ARG
+    assert library.gh_maxpool2d_nhwc(dummy, 0, dummy, 1, 8, 8, 6, 3, 2, 1, None) == _lib.GH_ERR_UNSUPPORTED                  # C % 4
+    assert library.gh_maxpool2d_nhwc(dummy, 0, dummy, 1, 8, 8, 64, 3, 2, 2, None) == _lib.GH_ERR_BAD_ARG                     # pad > k/2
+    assert library.gh_stem_space_to_depth(None, 1, 1, 1, 1, 1, 8, 8, None, 0, None) == _lib.GH_ERR_BAD_ARG
+    assert library.gh_stem_space_to_depth(dummy, 1, 1, 1, 1, 1, 7, 8, dummy, 0, None) == _lib.GH_ERR_UNSUPPORTED             # odd H
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

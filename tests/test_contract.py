@@ -222,3 +222,25 @@ def test_backbone_mode_defaults_and_validation(monkeypatch):
         m.set_backbone_mode("int8")
     monkeypatch.setenv("GRAMHEAD_BACKBONE", "bf16")
     assert TruncatedResNet50(models.resnet50(weights=None), 5, 4, 8, device="cpu").backbone_mode == "bf16"
+
+
+def test_inference_plan_is_off_without_cuda_and_never_changes_the_state_dict(monkeypatch):
+    monkeypatch.delenv("GRAMHEAD_FOLD_BN", raising=False)
+    m = build(trunc=5, g=8).eval()
+    assert m.fold_batchnorm is True and m._plan is None
+    keys = list(m.state_dict())
+    with torch.no_grad():
+        assert m._inference_plan(torch.randn(1, 3, 32, 32)) is None        # CPU tensor: children run one by one
+    m.set_backbone_mode("channels_last")
+    with torch.no_grad():
+        assert m._inference_plan(torch.randn(1, 3, 32, 32)) is None
+    assert list(m.state_dict()) == keys and not any(k.startswith("_plan") for k in keys)
+    from heuristique_style_transfer_code_b200.frozen_encoder import FoldedEncoder, encoder_signature
+    assert FoldedEncoder.supported(m.truncated_encoder)
+    sig = encoder_signature(m.truncated_encoder)
+    with torch.no_grad():
+        m.truncated_encoder[1].weight.mul_(2.0)
+    assert encoder_signature(m.truncated_encoder) != sig                   # in-place edits are seen
+    assert not FoldedEncoder.supported(torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3), torch.nn.ReLU()))
+    monkeypatch.setenv("GRAMHEAD_FOLD_BN", "0")
+    assert build(trunc=5, g=8).fold_batchnorm is False
