@@ -52,7 +52,7 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int, torch.d
     if use_cuda:
         torch.cuda.set_device(device)
         want = os.environ.get("GRAMHEAD_CPU_AFFINITY", "auto")
-        if want == "1" or (want == "auto" and world > 1):
+        if want in ("1", "auto"):
             bind_to_gpu_cpus(device)
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
