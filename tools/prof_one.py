@@ -1,5 +1,5 @@
 """Tiny single-kernel drivers for `ncu --set full` captures (a few launches, nothing else on the GPU).
-    python tools/prof_one.py bwd|fwd|gemm [C HW B [f32|bf16 [pair(-1|0|1) [nchw|nhwc]]]]"""
+    python tools/prof_one.py bwd|fwd|pool|gemm [C HW B [f32|bf16 [pair(-1|0|1) [nchw|nhwc]]]]"""
 import os
 import sys
 
@@ -31,6 +31,12 @@ if kind in ("bwd", "fwd"):
             ops.gram_pool_bwd(x, g, dd, 0)
         else:
             ops.gram_pool_fwd_(x, g, desc, 0)
+elif kind == "pool":                          # stem max pool of the inference plan: (B, 64, 112, 112) channels_last
+    y = torch.relu(torch.randn(B, 64, 112, 112, device="cuda")).contiguous(memory_format=torch.channels_last)
+    if dt == "bf16":
+        y = y.bfloat16()
+    for _ in range(4):
+        ops.maxpool2d_nhwc(y, 3, 2, 1)
 else:
     a = torch.randn(768, 1024, device="cuda")
     w = torch.randn(3072, 1024, device="cuda")

@@ -86,6 +86,11 @@ def rep_summary(tag, name):
                 u = units[idx[key]].lower()
                 return v * {"gbyte": 1e9, "mbyte": 1e6, "kbyte": 1e3, "byte": 1.0}.get(u, 1.0)
             traffic[kname] = int(val("dram__bytes_read.sum") + val("dram__bytes_write.sum"))
+            if name.startswith("pool_"):                       # tools/prof_one.py pool: (256, 64, 112, 112) channels_last
+                dt = "torch.float32" if name.endswith("f32") else "torch.bfloat16"
+                key = f"maxpool2d_nhwc[C=64,HW=112x112,{dt}]"
+                traffic[key] = traffic[kname]
+                ALGO[key] = int(256 * 64 * 112 * 112 * 1.25 * (4 if name.endswith("f32") else 2))
             m = re.match(r"(fwd|bwd)_(\d+)_(\d+)_(f32|bf16)_(nchw|nhwc)", name)     # capture names carry the bench's key
             if m:
                 dt = "torch.float32" if m.group(4) == "f32" else "torch.bfloat16"
