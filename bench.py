@@ -411,6 +411,20 @@ def run_ours(args):
                             "per_gpu_batch": hi - lo, "optimizer": "AdamW(lr=1e-3)",
                             "parallelism": f"ddp{world}" if world > 1 else "single"},
                  "kernels": tk, "roofline": troof}
+        if world > 1:
+            # The same step with the per-GPU batch held at the single-GPU size (weak scaling, global batch gb * world):
+            # at 512 / world images per GPU the cuDNN encoder's train-mode kernels stop shrinking with the shard
+            # (DESIGN section 6), which bounds the strong-scaling number above whatever the all-reduce costs.
+            del xt, yt
+            torch.manual_seed(200 + rank)
+            xt = torch.randn(gb, 3, IMAGE, IMAGE, device=device)
+            yt = torch.randint(0, NUM_CLASSES, (gb,), device=device)
+            for _ in range(2):
+                train_step()
+            wms = timed_region(train_step, tsteps, device, D)
+            train["weak_scaling"] = {"value": round(gb * world * tsteps / (wms / 1e3), 1), "unit": "images/s",
+                                     "ms_per_step": round(wms / tsteps, 2), "global_batch": gb * world,
+                                     "per_gpu_batch": gb, "steps": tsteps, "scaling": "weak"}
         del xt, yt, tmodel, ddp, opt
 
     if rank != 0:
