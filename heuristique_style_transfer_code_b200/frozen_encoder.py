@@ -76,9 +76,13 @@ def _is_bottleneck(block) -> bool:
     return ok
 
 
-def encoder_signature(encoder: nn.Module) -> Tuple:
-    """Changes whenever a parameter or buffer of the encoder is modified, replaced or moved."""
-    return tuple((t.data_ptr(), t._version) for t in list(encoder.parameters()) + list(encoder.buffers()))
+def encoder_signature(encoder: nn.Module) -> Optional[Tuple]:
+    """Changes whenever a parameter or buffer of the encoder is modified, replaced or moved. None when the tensors
+    carry no version counter (created under torch.inference_mode()): the plan is then not used at all."""
+    try:
+        return tuple((t.data_ptr(), t._version) for t in list(encoder.parameters()) + list(encoder.buffers()))
+    except RuntimeError:
+        return None
 
 
 class FoldedEncoder:

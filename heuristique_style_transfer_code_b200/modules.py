@@ -104,7 +104,10 @@ class _TruncatedGramAttentionBase(nn.Module):
             return None
         dtype = torch.bfloat16 if self._backbone_mode.startswith("bf16") else torch.float32
         plan = self._plan
-        if plan is None or plan.dtype != dtype or plan.signature != encoder_signature(enc):
+        signature = encoder_signature(enc)
+        if signature is None:
+            return None
+        if plan is None or plan.dtype != dtype or plan.signature != signature:
             plan = FoldedEncoder.build(enc, dtype, channels_last=True) if FoldedEncoder.supported(enc) else None
             self._plan = plan
         return plan
