@@ -244,3 +244,16 @@ def test_inference_plan_is_off_without_cuda_and_never_changes_the_state_dict(mon
     assert not FoldedEncoder.supported(torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3), torch.nn.ReLU()))
     monkeypatch.setenv("GRAMHEAD_FOLD_BN", "0")
     assert build(trunc=5, g=8).fold_batchnorm is False
+
+
+def test_host_collector_and_buffer_reusing_prefetch_on_cpu():
+    from heuristique_style_transfer_code_b200.functions import HostCollector, cuda_prefetch
+    c = HostCollector(depth=2)
+    for i in range(5):
+        c.push(torch.full((3, 2), float(i)), torch.tensor([i]))
+    out = c.finish()
+    assert [float(a[0, 0]) for a, _ in out] == [0.0, 1.0, 2.0, 3.0, 4.0] and [int(b[0]) for _, b in out] == list(range(5))
+    assert c.finish() == []
+    batches = [(torch.full((2, 3), float(i)), torch.tensor([i, i]), "meta") for i in range(4)]
+    got = list(cuda_prefetch(iter(batches), "cpu", reuse_buffers=True))
+    assert len(got) == 4 and all(torch.equal(g[0], b[0]) and g[2] == "meta" for g, b in zip(got, batches))
