@@ -265,20 +265,22 @@ def evaluate_model(model, val_loader, criterion, writer=None, fold=0):
     device = _default_device()
     model.to(device)
     model.eval()
-    loss_sum = 0.0
-    correct = torch.zeros((), dtype=torch.long, device=device)
-    preds_all, labels_all = [], []
+    results = HostCollector()
     with torch.no_grad():
         for inputs, labels in cuda_prefetch(val_loader, device, reuse_buffers=True):
             outputs = model(inputs)
-            loss_sum += criterion(outputs, labels).item() * inputs.size(0)
-            preds = outputs.argmax(dim=1)
-            correct += (preds == labels).sum()
-            preds_all.extend(preds.cpu().numpy())
-            labels_all.extend(labels.cpu().numpy())
+            # the reference reads loss.item() and the predictions after every batch (:160-166); here they ride to the
+            # host through the pinned ring and are reduced there afterwards, in the same order and precision
+            results.push(criterion(outputs, labels).reshape(1), outputs.argmax(dim=1), labels)
+    loss_sum, correct, preds_all, labels_all = 0.0, 0, [], []
+    for loss, preds, labels in results.finish():
+        loss_sum += float(loss[0]) * len(labels)
+        correct += int((preds == labels).sum())
+        preds_all.extend(preds)
+        labels_all.extend(labels)
     n = len(val_loader.dataset)
     total_loss = loss_sum / n
-    accuracy = correct.double() / n
+    accuracy = torch.tensor(correct, dtype=torch.float64) / n
     precision = precision_score(labels_all, preds_all, average='weighted', zero_division=0)
     recall = recall_score(labels_all, preds_all, average='weighted', zero_division=0)
     print(f'Fold {fold}, Validation Loss: {total_loss:.4f}, Accuracy: {accuracy:.4f}, Precision: {precision:.4f}, '
