@@ -115,3 +115,24 @@ def test_structure_and_loud_failures_without_cuda():
     with torch.no_grad():
         e, o = patchgan_multiscale_forward(ms.eval(), torch.randn(1, 3, 224, 224))
     assert e.shape == (1, 16) and o.shape == (1, 10)
+
+
+@needs_reference
+def test_reference_scripts_resolve_the_drop_in_classes_and_keep_their_own_functions_file():
+    """What tools/run_ref_script.py arranges for test_Multi_PatchGAN.py: the model classes come from this repository,
+    functions.functions_Multi_PatchGAN (not provided here) from the reference tree through the namespace packages."""
+    import subprocess
+    import sys
+    from oracle.ref_loader import REFERENCE_ROOT
+    code = (
+        "import sys, importlib.util\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "import Models.Models_Multi_PatchGAN as mine\n"
+        f"sys.path.insert(0, {REFERENCE_ROOT!r})\n"
+        "from Models.Models_Multi_PatchGAN import MultiScaleDiscriminator_test as cls\n"
+        "assert cls is mine.MultiScaleDiscriminator_test and cls.__module__.startswith('heuristique_style_transfer_code_b200')\n"
+        "spec = importlib.util.find_spec('functions.functions_Multi_PatchGAN')\n"
+        f"assert spec is not None and spec.origin.startswith({REFERENCE_ROOT!r}), spec\n"
+        "print('ok')\n")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr

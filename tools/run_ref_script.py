@@ -41,7 +41,11 @@ def run():
     # import the drop-in packages first: runpy prepends the script's directory (the reference tree, which has its own
     # Models/ and functions/ namespace dirs) to sys.path, but modules already in sys.modules are not looked up again.
     import Models.Models_RESNET50_TRUNCATE_GRAM_with_Attention  # noqa: F401
+    import Models.Models_Multi_PatchGAN  # noqa: F401
     import functions.functions_RESNET50_Truncate_Gram_Attention  # noqa: F401
+    # modules this repository does not provide (e.g. functions.functions_Multi_PatchGAN, which the Multi-PatchGAN scripts
+    # import next to the model classes) still resolve to the reference's files: Models/ and functions/ are namespace
+    # packages in both trees, so Python merges the two directories.
     runpy.run_path(script, run_name="__main__")
 
 
