@@ -150,7 +150,7 @@ def summarise_profile(records, peaks):
     return kernels, roof
 
 
-def patchgan_leg(device, peaks, steps, batch=64):
+def patchgan_leg(device, peaks, steps, batch=256):
     """MultiScaleDiscriminator_test (ndf 64, gram_matrix_dim 64, batch norm, patches 10/70/150) on `batch` 224x224 images:
     this repo's classes (cuDNN extractor + the library's head kernels) and the op-for-op torch port of the reference
     forward, same GPU, same weights, eval + no_grad. The head's dominant kernel is the pooling pass (HBM-bound)."""
