@@ -432,6 +432,7 @@ def run_ours(args):
 
     cpu_base = None
     if world == 1 and not args.skip_cpu:
+        D.restore_cpu_affinity()                  # the CPU baseline gets every host core, not only the GPU-local ones
         cores = os.cpu_count() or 1
         sample = 16
         ips, sec = cpu_reference_forward(B, sample, 6, 2, cores)

@@ -19,6 +19,15 @@ import torch
 import torch.distributed as dist
 
 
+ORIGINAL_AFFINITY = None          # the process's CPU set before bind_to_gpu_cpus() narrowed it (restore_cpu_affinity())
+
+
+def restore_cpu_affinity() -> None:
+    """Gives the process back every CPU it had at start (host-side work that should use all cores, e.g. a CPU baseline)."""
+    if ORIGINAL_AFFINITY is not None:
+        os.sched_setaffinity(0, ORIGINAL_AFFINITY)
+
+
 def bind_to_gpu_cpus(device: torch.device) -> Optional[Sequence[int]]:
     """Pins this process to the CPU cores NVML reports as local to `device` (same NUMA node / PCIe root), so the pinned
     staging buffers it allocates afterwards and its launch thread sit next to the GPU. With several ranks on a
@@ -36,6 +45,9 @@ def bind_to_gpu_cpus(device: torch.device) -> Optional[Sequence[int]]:
         cpus &= os.sched_getaffinity(0)
         if not cpus:
             return None
+        global ORIGINAL_AFFINITY
+        if ORIGINAL_AFFINITY is None:
+            ORIGINAL_AFFINITY = os.sched_getaffinity(0)
         os.sched_setaffinity(0, cpus)
         return sorted(cpus)
     except Exception:
