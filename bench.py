@@ -151,45 +151,34 @@ def summarise_profile(records, peaks):
 
 
 def patchgan_leg(device, peaks, steps, batch=256):
-    """MultiScaleDiscriminator_test (ndf 64, gram_matrix_dim 64, batch norm, patches 10/70/150) on `batch` 224x224 images:
-    this repo's classes (cuDNN extractor + the library's head kernels) and the op-for-op torch port of the reference
-    forward, same GPU, same weights, eval + no_grad. The head's dominant kernel is the pooling pass (HBM-bound)."""
+    """MultiScaleDiscriminator_test (ndf 64, gram_matrix_dim 64, batch norm, patches 10/70/150) on `batch` 224x224 images,
+    eval + no_grad: cuDNN extractor + the library's head kernels. The head's dominant launch is the pooling pass
+    (HBM-bound). Parity against the reference's op sequence is checked in tests/test_gpu_patchgan.py and smoke(); its
+    timing on the same GPU is in profiles/r01x_patchgan_head_summary.md (tests/tools/bench_patchgan.py)."""
     from heuristique_style_transfer_code_b200 import ops
     from heuristique_style_transfer_code_b200.patchgan import MultiScaleDiscriminator_test
-    from oracle.torch_port import patchgan_multiscale_forward
     torch.manual_seed(0)
     m = MultiScaleDiscriminator_test(ndf=64, norm='batch', num_classes=NUM_CLASSES, gram_matrix_dim=64).to(device).eval()
     x = torch.randn(batch, 3, IMAGE, IMAGE, device=device)
-
-    def timed(fn):
+    with torch.no_grad():
         for _ in range(3):
-            fn()
+            m(x)
         torch.cuda.synchronize(device)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        saved, ops.PROFILE = ops.PROFILE, []
         s.record()
         for _ in range(steps):
-            fn()
+            emb, out = m(x)
         e.record()
         torch.cuda.synchronize(device)
-        return s.elapsed_time(e) / steps
-
-    with torch.no_grad():
-        ours = timed(lambda: m(x))
-        port = timed(lambda: patchgan_multiscale_forward(m, x))
-        saved, ops.PROFILE = ops.PROFILE, []
-        for _ in range(steps):
-            e1, o1 = m(x)
-        torch.cuda.synchronize(device)
         rec, ops.PROFILE = ops.PROFILE, saved
-        e2, o2 = patchgan_multiscale_forward(m, x)
+    ours = s.elapsed_time(e) / steps
     kernels, roof = summarise_profile(rec, peaks)
     head_ms = sum(k["total_ms"] for k in kernels.values()) / steps
     return {"workload": f"MultiScaleDiscriminator_test ndf 64, gram_matrix_dim 64, 3 scales, batch {batch} at {IMAGE}x{IMAGE}, "
                         "eval/no_grad", "images_per_s": round(batch / ours * 1e3, 1), "ms_per_step": round(ours, 3),
-            "torch_port_same_gpu_ms": round(port, 3), "torch_port_images_per_s": round(batch / port * 1e3, 1),
-            "head_kernels_ms": round(head_ms, 3), "embeddings_rel_diff_vs_port": float((e1 - e2).norm() / e2.norm()),
-            "output_rel_diff_vs_port": float((o1 - o2).norm() / o2.norm()),
-            "argmax_equal": bool((o1.argmax(1) == o2.argmax(1)).all()), "kernels": kernels, "roofline": roof}
+            "head_kernels_ms": round(head_ms, 3), "finite": bool(torch.isfinite(emb).all() and torch.isfinite(out).all()),
+            "kernels": kernels, "roofline": roof}
 
 
 def cpu_reference_forward(batch, sample, steps, warmup, threads):

@@ -1,12 +1,12 @@
 """Multi-PatchGAN Gram head on one B200: MultiScaleDiscriminator_test (ndf 64, gram_matrix_dim 64,
 batch norm, patches 10/70/150) at 224x224, this repo's classes against the fp32 torch port of the reference forward on
 the same GPU and weights; per-kernel times and achieved bandwidth of the head kernels.
-    python tools/bench_patchgan.py [batch] [steps]"""
+    python tests/tools/bench_patchgan.py [batch] [steps]"""
 import json
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 

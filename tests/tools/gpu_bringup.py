@@ -1,5 +1,5 @@
 """GPU bring-up / diagnostics: each case runs in its own process (a device trap poisons the CUDA context) and prints
-normwise errors against the fp64 oracle. Usage on a B200:  python tools/gpu_bringup.py [case ...]   (default: all)"""
+normwise errors against the fp64 oracle. Usage on a B200:  python tests/tools/gpu_bringup.py [case ...]   (default: all)"""
 from __future__ import annotations
 
 import os
@@ -7,7 +7,7 @@ import subprocess
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 CASES = {}

@@ -6,10 +6,10 @@ OUT=gpurun_out; mkdir -p $OUT
 TAG=${1:-r}
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/${TAG}_gpu.txt 2>&1
 lscpu | grep -E "Model name|^CPU\(s\)|Thread|Socket" >> $OUT/${TAG}_gpu.txt 2>&1
-timeout 900 python tools/gpu_bringup.py pair_fwd_min pair_bwd_min pair_bwd pair_bwd_dense > $OUT/${TAG}_bringup.log 2>&1
+timeout 900 python tests/tools/gpu_bringup.py pair_fwd_min pair_bwd_min pair_bwd pair_bwd_dense > $OUT/${TAG}_bringup.log 2>&1
 rc=$?
 echo "bringup exit=$rc"; grep -E "pair-|PASS|FAIL|SUMMARY|rror|device error" $OUT/${TAG}_bringup.log | head -60
-timeout 600 python tools/gpu_bringup.py timing_pair > $OUT/${TAG}_timing_pair.log 2>&1
+timeout 600 python tests/tools/gpu_bringup.py timing_pair > $OUT/${TAG}_timing_pair.log 2>&1
 echo "timing exit=$?"; grep -E "^bwd.*pair=1|^fwd.*pair=1|PASS|FAIL" $OUT/${TAG}_timing_pair.log | head -80
 [ "$rc" = "0" ] || exit 1
 echo "== pytest -m gpu"; timeout 1800 python -m pytest tests -x -q -m gpu > $OUT/${TAG}_pytest_gpu.log 2>&1; echo "pytest exit=$?"; tail -8 $OUT/${TAG}_pytest_gpu.log
