@@ -50,6 +50,15 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (kernels launched with launch_pdl(), gramhead.cu): the next kernel of a chain may
+// start -- run its prologue, become resident -- while this one is still executing; pdl_wait() blocks until every
+// prerequisite grid has completed and its memory is visible. Every thread calls pdl_wait() before it touches global
+// memory a predecessor wrote (or will read: a successor never writes before its own wait).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {

@@ -9,6 +9,8 @@
 #include "gram_bwd_pair.cuh"
 #include "attn_head.cuh"
 #include "umma_gemm.cuh"
+#include "tgemm_pair.cuh"
+#include "attn_head2.cuh"
 #include "preprocess.cuh"
 #include "transpose.cuh"
 #include "patchgan.cuh"
@@ -486,6 +488,11 @@ int gh_set_option(const char* name, int value) {
     g_opt_fwd_epilogue_warps = value;
     return 0;
   }
+  if (key == "pdl") {
+    if (value != 0 && value != 1) return GH_ERR_BAD_ARG;
+    g_opt_pdl = value;
+    return 0;
+  }
   if (key == "attn_gemm") {
     if (value != 0 && value != 1) return GH_ERR_BAD_ARG;
     g_opt_attn_gemm = value;
@@ -731,6 +738,163 @@ int gh_patch_attn_fwd(const float* feat, const float* W_in1, const float* b_in1,
   const int sms = gh_sm_count();
   const int grid = B < 4 * sms ? B : 4 * sms;
   patch_attention_kernel<<<grid, kPatchThreads, smem, (cudaStream_t)stream>>>(p);
+  return (int)cudaGetLastError();
+}
+
+// ---- attention head on the TMA-fed split-bf16 GEMMs (tgemm_pair.cuh, attn_head2.cuh) --------------------------------
+static bool attn2_supported(int B, int L, int E, int nc) {
+  return B > 0 && L > 0 && L <= kMaxL && E >= 64 && E % 64 == 0 && E <= 4 * kAttn2Threads && nc > 0 && nc <= kAttn2MaxNc &&
+         sm_count_cached() >= 2;
+}
+static TgOperand tg_op(const void* planes, long long ld, long long rows_total, int mn_major) {
+  TgOperand o;
+  o.planes = planes; o.ld = ld; o.plane_stride = ld * rows_total; o.mn_major = mn_major;
+  return o;
+}
+static TgSpec tg_spec(TgOperand A, TgOperand Bo, int M, int N, int K, const float* bias, float* D, long long ldd,
+                      int max_split) {
+  TgSpec s{};
+  s.A = A; s.B = Bo; s.M = M; s.N = N; s.K = K; s.bias = bias; s.D_f32 = D; s.D_planes = nullptr; s.ldd = ldd;
+  s.d_plane_stride = 0; s.max_split = max_split; s.tn = 256; s.ksplit = 1;
+  return s;
+}
+
+int gh_split_bf16(const float* src, void* planes, long long n, long long plane_stride, void* stream) {
+  if (!src || !planes || n <= 0 || plane_stride < n) return GH_ERR_BAD_ARG;
+  if (n % 4 != 0 || plane_stride % 4 != 0 || (uintptr_t)src % 16 != 0 || (uintptr_t)planes % 8 != 0) return GH_ERR_UNSUPPORTED;
+  const long long n4 = n / 4;
+  long long blocks = (n4 + 255) / 256;
+  const long long cap = (long long)sm_count_cached() * 16;
+  if (blocks > cap) blocks = cap;
+  return (int)launch_pdl(split_bf16_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, src,
+                         (__nv_bfloat16*)planes, n4, plane_stride);
+}
+
+int gh_gemm_planes(const void* A_planes, long long lda, long long a_plane_stride, int a_mn, const void* B_planes,
+                   long long ldb, long long b_plane_stride, int b_mn, const float* bias, float* D, void* D_planes,
+                   long long ldd, long long d_plane_stride, int M, int N, int K, int max_split, void* stream) {
+  if (!A_planes || !B_planes || (!D && !D_planes) || (D && D_planes) || M <= 0 || N <= 0 || K <= 0) return GH_ERR_BAD_ARG;
+  TgSpec s{};
+  s.A.planes = A_planes; s.A.ld = lda; s.A.plane_stride = a_plane_stride; s.A.mn_major = a_mn ? 1 : 0;
+  s.B.planes = B_planes; s.B.ld = ldb; s.B.plane_stride = b_plane_stride; s.B.mn_major = b_mn ? 1 : 0;
+  s.M = M; s.N = N; s.K = K; s.bias = bias; s.D_f32 = D; s.D_planes = D_planes; s.ldd = ldd;
+  s.d_plane_stride = d_plane_stride; s.max_split = D_planes ? 1 : (max_split < 1 ? 1 : max_split);
+  const int sms = sm_count_cached();
+  if (sms < 2) return GH_ERR_UNSUPPORTED;
+  tg_plan(&s, 1, sms / 2);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e;
+  if (s.ksplit > 1) {
+    e = cudaMemset2DAsync(D, (size_t)ldd * 4, 0, (size_t)N * 4, (size_t)M, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  e = launch_tgemm(&s, 1, sms, st);
+  return e == cudaErrorNotSupported ? GH_ERR_UNSUPPORTED : (int)e;
+}
+
+int gh_attn_head_fwd2(const float* desc, const void* w_in_planes, const float* b_in, const void* w_out_planes,
+                      const float* b_out, const float* W_c, const float* b_c, int B, int L, int E, int nc, void* x_planes,
+                      float* qkv, float* probs, void* obar_planes, float* emb, float* logits, void* stream) {
+  if (!desc || !w_in_planes || !w_out_planes || !W_c || !x_planes || !qkv || !probs || !obar_planes || !emb || !logits)
+    return GH_ERR_BAD_ARG;
+  if (B <= 0 || L <= 0 || E <= 0 || nc <= 0) return GH_ERR_BAD_ARG;
+  if (!attn2_supported(B, L, E, nc)) return GH_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int sms = sm_count_cached();
+  const long long BL = (long long)B * L;
+  // X -> planes (the A operand of the in_proj GEMM, and of dW_in in the backward)
+  int rc = gh_split_bf16(desc, x_planes, BL * E, BL * E, stream);
+  if (rc != 0) return rc;
+  // QKV = X W_in^T + b_in           (B*L, 3E); at most two K partitions, so the sum is bitwise reproducible
+  TgSpec s1 = tg_spec(tg_op(x_planes, E, BL, 0), tg_op(w_in_planes, E, 3LL * E, 0), (int)BL, 3 * E, E, b_in, qkv, 3LL * E, 2);
+  tg_plan(&s1, 1, sms / 2);
+  cudaError_t e;
+  if (s1.ksplit > 1) {
+    e = cudaMemsetAsync(qkv, 0, (size_t)BL * 3 * E * 4, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  e = launch_tgemm(&s1, 1, sms, st);
+  if (e != cudaSuccess) return e == cudaErrorNotSupported ? GH_ERR_UNSUPPORTED : (int)e;
+  // emb = Obar W_out^T + b_out      (B, E)
+  TgSpec s2 = tg_spec(tg_op(obar_planes, E, B, 0), tg_op(w_out_planes, E, E, 0), B, E, E, b_out, emb, E, 2);
+  tg_plan(&s2, 1, sms / 2);
+  __nv_bfloat16* ob = (__nv_bfloat16*)obar_planes;
+  float* ez = s2.ksplit > 1 ? emb : nullptr;
+  if (L <= 4) e = launch_pdl(attn2_core_fwd_kernel<4>, dim3(B), dim3(kAttn2Threads), 0, st, qkv, probs, ob, (long long)B * E, ez, L, E);
+  else e = launch_pdl(attn2_core_fwd_kernel<kMaxL>, dim3(B), dim3(kAttn2Threads), 0, st, qkv, probs, ob, (long long)B * E, ez, L, E);
+  if (e != cudaSuccess) return (int)e;
+  e = launch_tgemm(&s2, 1, sms, st);
+  if (e != cudaSuccess) return e == cudaErrorNotSupported ? GH_ERR_UNSUPPORTED : (int)e;
+  return (int)launch_pdl(attn2_classifier_kernel, dim3((B + 3) / 4), dim3(128), 0, st, emb, W_c, b_c, logits, B, E, nc);
+}
+
+long long gh_attn_head_bwd2_workspace(int B, int L, int E) {
+  if (B <= 0 || L <= 0 || E <= 0) return 0;
+  // bytes: demb planes (2 * B*E bf16) | dobar fp32 (B*E) | dQKV planes (2 * B*L*3E bf16) | db_in scratch (3E fp32)
+  return 4LL * B * E + 4LL * B * E + 12LL * B * L * E + 12LL * E;
+}
+
+int gh_attn_head_bwd2(const void* x_planes, const void* w_in_planes, const void* w_out_planes, const float* W_c,
+                      const float* qkv, const float* probs, const void* obar_planes, const float* emb,
+                      const float* d_logits, const float* d_emb_ext, int B, int L, int E, int nc, float* d_desc,
+                      float* dW_in, float* db_in, float* dW_out, float* db_out, float* dW_c, float* db_c, void* workspace,
+                      void* stream) {
+  if (!x_planes || !w_in_planes || !w_out_planes || !W_c || !qkv || !probs || !obar_planes || !emb || !d_logits || !workspace)
+    return GH_ERR_BAD_ARG;
+  if (B <= 0 || L <= 0 || E <= 0 || nc <= 0) return GH_ERR_BAD_ARG;
+  if (!attn2_supported(B, L, E, nc) || (uintptr_t)workspace % 16 != 0) return GH_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int sms = sm_count_cached();
+  const long long BL = (long long)B * L, BE = (long long)B * E;
+  uint8_t* ws = (uint8_t*)workspace;
+  __nv_bfloat16* demb = (__nv_bfloat16*)ws;                       // planes (B, E)
+  float* dobar = (float*)(ws + 4 * BE);                           // (B, E)
+  __nv_bfloat16* dqkv = (__nv_bfloat16*)(ws + 8 * BE);            // planes (B*L, 3E)
+  float* dbin_scratch = (float*)(ws + 8 * BE + 12 * BL * E);      // (3E) when the caller does not want db_in
+
+  // G1: dObar = demb W_out (B, E) and dW_out = demb^T Obar (E, E)
+  TgSpec g1[2];
+  int n1 = 0;
+  g1[n1++] = tg_spec(tg_op(demb, E, B, 0), tg_op(w_out_planes, E, E, 1), B, E, E, nullptr, dobar, E, 64);
+  if (dW_out) g1[n1++] = tg_spec(tg_op(demb, E, B, 1), tg_op(obar_planes, E, B, 1), E, E, B, nullptr, dW_out, E, 64);
+  tg_plan(g1, n1, sms / 2);
+  // G2: dW_in = dQKV^T X (3E, E) and dX = dQKV W_in (B*L, E)
+  TgSpec g2[2];
+  int n2 = 0;
+  if (dW_in) g2[n2++] = tg_spec(tg_op(dqkv, 3LL * E, BL, 1), tg_op(x_planes, E, BL, 1), 3 * E, E, (int)BL, nullptr, dW_in, E, 64);
+  if (d_desc) g2[n2++] = tg_spec(tg_op(dqkv, 3LL * E, BL, 0), tg_op(w_in_planes, E, 3LL * E, 1), (int)BL, E, 3 * E, nullptr, d_desc, E, 64);
+  if (n2) tg_plan(g2, n2, sms / 2);
+
+  float* dbin = db_in ? db_in : dbin_scratch;
+  ZeroList z0{};
+  z0.ptr[0] = g1[0].ksplit > 1 ? dobar : nullptr; z0.n4[0] = BE / 4;
+  z0.ptr[1] = (n1 > 1 && g1[1].ksplit > 1) ? dW_out : nullptr; z0.n4[1] = (long long)E * E / 4;
+  z0.ptr[2] = dbin; z0.n4[2] = 3LL * E / 4;
+  const size_t prep_smem = attn2_prep_smem_bytes(nc);
+  cudaError_t e = cudaSuccess;
+  if (prep_smem > 48 * 1024) {
+    e = cudaFuncSetAttribute(attn2_bwd_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  e = launch_pdl(attn2_bwd_prep_kernel, dim3((E + 127) / 128, kPrepSplit), dim3(kPrepThreads), prep_smem, st, d_logits,
+                 d_emb_ext, W_c, emb, demb, BE, db_out, dW_c, db_c, B, E, nc, z0);
+  if (e != cudaSuccess) return (int)e;
+  e = launch_tgemm(g1, n1, sms, st);
+  if (e != cudaSuccess) return e == cudaErrorNotSupported ? GH_ERR_UNSUPPORTED : (int)e;
+  ZeroList z1{};
+  for (int i = 0; i < n2; ++i) {
+    z1.ptr[i] = g2[i].ksplit > 1 ? g2[i].D_f32 : nullptr;
+    z1.n4[i] = (long long)g2[i].M * g2[i].N / 4;
+  }
+  int grid = 2 * sms;                              // one resident wave; each CTA adds its db_in column sums once
+  if (grid > B) grid = B;
+  if (L <= 4) e = launch_pdl(attn2_core_bwd_kernel<4>, dim3(grid), dim3(kAttn2Threads), 0, st, qkv, probs, (const float*)dobar, dqkv, BL * 3 * E, dbin, B, L, E, z1);
+  else e = launch_pdl(attn2_core_bwd_kernel<kMaxL>, dim3(grid), dim3(kAttn2Threads), 0, st, qkv, probs, (const float*)dobar, dqkv, BL * 3 * E, dbin, B, L, E, z1);
+  if (e != cudaSuccess) return (int)e;
+  if (n2) {
+    e = launch_tgemm(g2, n2, sms, st);
+    if (e != cudaSuccess) return e == cudaErrorNotSupported ? GH_ERR_UNSUPPORTED : (int)e;
+  }
   return (int)cudaGetLastError();
 }
 

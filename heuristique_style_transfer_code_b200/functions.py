@@ -452,105 +452,26 @@ def load_hyperparameters(hyperparams_path):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# t-SNE views (:343-474): CPU/GUI post-processing of the embeddings, outside the accelerated path; kept so that the
-# reference's test script imports resolve and the non-interactive plot works when matplotlib is installed.
+# t-SNE views (:343-474): CPU/GUI post-processing of the embeddings (sklearn + matplotlib + Tk), outside the accelerated
+# path. The names resolve for the reference's test script; the calls are delegated to the reference's own file.
 # ---------------------------------------------------------------------------------------------------------------------
-def _label_colors(labels, colors, plt):
-    unique = np.unique(labels)
-    if colors and len(colors) >= len(unique):
-        return unique, {label: colors[i] for i, label in enumerate(unique)}
-    palette = plt.cm.get_cmap("tab20", len(unique))
-    return unique, {label: palette(label) for label in unique}
+_REF_FUNCTIONS = os.path.join("functions", "functions_RESNET50_Truncate_Gram_Attention.py")
 
 
 def perform_tsne(embeddings, labels, save_path, colors=None):
-    from sklearn.manifold import TSNE
-    import matplotlib.pyplot as plt
-    points = TSNE(n_components=2, random_state=0).fit_transform(embeddings)
-    plt.figure(figsize=(10, 10))
-    unique, cmap = _label_colors(labels, colors, plt)
-    for label in unique:
-        sel = labels == label
-        plt.scatter(points[sel, 0], points[sel, 1], label=f'Class {label}', color=cmap[int(label)])
-    plt.legend()
-    plt.title('t-SNE of Embeddings')
-    plt.savefig(save_path)
-    plt.show()
-    print(f"t-SNE visualization saved to {save_path}")
+    from ._reference import load_reference_file
+    return load_reference_file(_REF_FUNCTIONS).perform_tsne(embeddings, labels, save_path, colors)
 
 
 def create_onpick_function(dataset, img_paths, img_label, label_text, classes, labels):
-    def onpick(event):
-        from PIL import Image, ImageTk
-        idx = event.ind[0]
-        print(f"Selected img_path: {img_paths[idx]}")
-        picture = ImageTk.PhotoImage(Image.open(img_paths[idx]).resize((400, 400), Image.LANCZOS))
-        img_label.configure(image=picture)
-        img_label.image = picture
-        label_text.set(f"Label: {classes[int(labels[idx])]}")
-    return onpick
+    from ._reference import load_reference_file
+    return load_reference_file(_REF_FUNCTIONS).create_onpick_function(dataset, img_paths, img_label, label_text, classes,
+                                                                      labels)
 
 
 def plot_tsne_interactive(embeddings, labels, classes, img_paths, dataset, colors=None):
-    """Tk window with a pickable t-SNE scatter and a polygon selector (:377-474). Needs tkinter + matplotlib."""
-    from sklearn.manifold import TSNE
-    import tkinter as tk
-    import matplotlib.pyplot as plt
-    from matplotlib.backends.backend_tkagg import FigureCanvasTkAgg
-    from matplotlib.widgets import PolygonSelector
-    from matplotlib.path import Path
-
-    points = TSNE(n_components=2, random_state=42).fit_transform(embeddings)
-    root = tk.Tk()
-    root.title("Interactive t-SNE with Images")
-    fig, ax = plt.subplots(figsize=(10, 10))
-    unique, cmap = _label_colors(labels, colors, plt)
-    scatter = ax.scatter(points[:, 0], points[:, 1], c=[cmap[int(v)] for v in labels], picker=True)
-    ax.legend(handles=scatter.legend_elements()[0], labels=[classes[int(v)] for v in unique])
-    img_label = tk.Label(root)
-    img_label.grid(row=0, column=1, sticky='nsew')
-    label_text = tk.StringVar()
-    tk.Label(root, textvariable=label_text).grid(row=1, column=1, sticky='nsew')
-    fig.canvas.mpl_connect('pick_event', create_onpick_function(dataset, img_paths, img_label, label_text, classes, labels))
-    canvas = FigureCanvasTkAgg(fig, master=root)
-    canvas.draw()
-    canvas.get_tk_widget().grid(row=0, column=0, rowspan=2, sticky='nsew')
-
-    state = {"polygon": [], "selector": None, "cleared": True}
-
-    def on_select(vertices):
-        state["polygon"] = list(vertices)
-        print("Polygon vertices:", vertices)
-
-    def on_button(event):
-        if event.button == 3 and (state["selector"] is None or state["cleared"]):
-            state["selector"] = PolygonSelector(ax, onselect=on_select, useblit=True)
-            state["cleared"] = False
-            print("Polygon selector enabled.")
-
-    def analyze():
-        if len(state["polygon"]) < 3:
-            print("Polygon not closed. Select at least 3 points.")
-            return
-        region = Path(state["polygon"])
-        inside = sum(1 for x, y in points if region.contains_point((x, y)))
-        print(f"Points inside polygon: {inside}")
-
-    def clear():
-        state["polygon"] = []
-        if state["selector"] is not None:
-            state["selector"].disconnect_events()
-            state["selector"].set_visible(False)
-            state["selector"] = None
-        while ax.patches:
-            ax.patches.pop().remove()
-        fig.canvas.draw()
-        state["cleared"] = True
-
-    fig.canvas.mpl_connect('button_press_event', on_button)
-    tk.Button(root, text="Close Polygon", command=analyze).grid(row=4, column=0, sticky='ew')
-    tk.Button(root, text="Clear Polygon", command=clear).grid(row=4, column=1, sticky='ew')
-    root.mainloop()
+    from ._reference import load_reference_file
+    return load_reference_file(_REF_FUNCTIONS).plot_tsne_interactive(embeddings, labels, classes, img_paths, dataset, colors)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

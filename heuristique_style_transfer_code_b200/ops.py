@@ -406,8 +406,55 @@ def style_descriptor(stages: Sequence[torch.Tensor], g: int) -> torch.Tensor:
     return _StyleDescriptor.apply(g, *stages)
 
 
+# Which kernels run the attention head: "tma" = TMA-fed split-bf16 GEMMs on CTA pairs (gh_attn_head_fwd2 / _bwd2) when
+# the shape allows it (E % 64 == 0, E <= 1024, L <= 8, nc <= 16), "ldg" = always the ld.global-fed kernels.
+ATTN_IMPL = "tma"
+
+
+def attn2_supported(L: int, e: int, nc: int) -> bool:
+    return ATTN_IMPL == "tma" and e % 64 == 0 and 64 <= e <= 1024 and 1 <= L <= 8 and 1 <= nc <= 16
+
+
+def split_bf16(x: torch.Tensor) -> torch.Tensor:
+    """fp32 tensor -> (2, *x.shape) bf16 planes: hi = bf16(x), lo = bf16(x - hi) (gh_split_bf16)."""
+    _require_cuda(x, "x")
+    x = x.detach().contiguous().float()
+    n = x.numel()
+    planes = torch.empty((2,) + tuple(x.shape), device=x.device, dtype=torch.bfloat16)
+    with torch.cuda.device(x.device), _Timed(f"split_bf16[n={n}]", 1, x.device, bytes=n * 8, flops=0, kind="split"):
+        rc = _lib.lib().gh_split_bf16(x.data_ptr(), planes.data_ptr(), n, n, _stream_ptr(x))
+    check(rc, "gh_split_bf16")
+    return planes
+
+
+# Split planes of the attention weights, one entry per parameter object, rebuilt when the parameter's version counter or
+# storage changes (optimizer steps, load_state_dict, .to()). Edits through `.data` bypass the counter: call
+# clear_weight_planes() after them.
+_WEIGHT_PLANES = {}
+
+
+def clear_weight_planes() -> None:
+    _WEIGHT_PLANES.clear()
+
+
+def weight_planes(w: torch.Tensor) -> torch.Tensor:
+    import weakref
+    key = id(w)
+    hit = _WEIGHT_PLANES.get(key)
+    if hit is not None:
+        ref, version, ptr, planes = hit
+        if ref() is w and version == w._version and ptr == w.data_ptr() and planes.device == w.device:
+            return planes
+    if len(_WEIGHT_PLANES) > 64:                       # parameters of models that no longer exist
+        for k in [k for k, v in _WEIGHT_PLANES.items() if v[0]() is None]:
+            del _WEIGHT_PLANES[k]
+    planes = split_bf16(w)
+    _WEIGHT_PLANES[key] = (weakref.ref(w), w._version, w.data_ptr(), planes)
+    return planes
+
+
 class _AttnHead(torch.autograd.Function):
-    """(B, L, E) descriptors + the six head parameters -> (embeddings (B, E), logits (B, nc))."""
+    """(B, L, E) descriptors + the six head parameters -> (embeddings (B, E), logits (B, nc)); ld.global-fed kernels."""
 
     @staticmethod
     def forward(ctx, desc, w_in, b_in, w_out, b_out, w_c, b_c):
@@ -424,7 +471,7 @@ class _AttnHead(torch.autograd.Function):
         logits = torch.empty((b, nc), device=dev, dtype=torch.float32)
         work = dict(bytes=(3 * e * e + e * e + nc * e) * 4 + b * L * e * 4 * 5, kind="attn",
                     flops=2 * b * L * e * 3 * e + 2 * b * e * e + 2 * b * e * nc + 4 * b * L * L * e)
-        with torch.cuda.device(dev), _Timed(f"attn_head_fwd[B={b},L={L},E={e}]", 4, dev, **work):
+        with torch.cuda.device(dev), _Timed(f"attn_head_fwd[B={b},L={L},E={e},ldg]", 4, dev, **work):
             rc = _lib.lib().gh_attn_head_fwd(desc.data_ptr(), *[p.data_ptr() for p in ps], b, L, e, nc, qkv.data_ptr(),
                                              probs.data_ptr(), obar.data_ptr(), emb.data_ptr(), logits.data_ptr(),
                                              _stream_ptr(desc))
@@ -454,7 +501,7 @@ class _AttnHead(torch.autograd.Function):
         ptr = lambda t: 0 if t is None else t.data_ptr()
         work = dict(bytes=(3 * e * e + e * e + nc * e) * 4 * 2 + b * L * e * 4 * 8, kind="attn",
                     flops=2 * (2 * b * L * e * 3 * e + 2 * b * e * e + 2 * b * e * nc) + 8 * b * L * L * e)
-        with torch.cuda.device(dev), _Timed(f"attn_head_bwd[B={b},L={L},E={e}]", 10, dev, **work):
+        with torch.cuda.device(dev), _Timed(f"attn_head_bwd[B={b},L={L},E={e},ldg]", 10, dev, **work):
             rc = lib.gh_attn_head_bwd(desc.data_ptr(), w_in.data_ptr(), w_out.data_ptr(), w_c.data_ptr(), qkv.data_ptr(),
                                       probs.data_ptr(), obar.data_ptr(), emb.data_ptr(), d_logits.data_ptr(), ptr(d_emb),
                                       b, L, e, nc, ptr(d_desc), ptr(gw_in), ptr(gb_in), ptr(gw_out), ptr(gb_out),
@@ -463,5 +510,96 @@ class _AttnHead(torch.autograd.Function):
         return d_desc, gw_in, gb_in, gw_out, gb_out, gw_c, gb_c
 
 
+class _AttnHead2(torch.autograd.Function):
+    """Same function on the TMA-fed GEMMs (gh_attn_head_fwd2 / gh_attn_head_bwd2). w_in_planes / w_out_planes are the
+    cached split planes of in_proj_weight / out_proj.weight (weight_planes())."""
+
+    @staticmethod
+    def forward(ctx, desc, w_in, b_in, w_out, b_out, w_c, b_c, w_in_planes, w_out_planes):
+        _require_cuda(desc, "descriptors")
+        desc = desc.contiguous().float()
+        b_in_, b_out_, w_c_, b_c_ = [t.contiguous().float() for t in (b_in, b_out, w_c, b_c)]
+        b, L, e = desc.shape
+        nc = w_c_.shape[0]
+        dev = desc.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        x_planes = torch.empty((2, b * L, e), device=dev, dtype=torch.bfloat16)
+        obar_planes = torch.empty((2, b, e), device=dev, dtype=torch.bfloat16)
+        qkv = torch.empty((b * L, 3 * e), **f32)
+        probs = torch.empty((b, L, L), **f32)
+        emb = torch.empty((b, e), **f32)
+        logits = torch.empty((b, nc), **f32)
+        work = dict(bytes=(3 * e * e + e * e + nc * e) * 4 + b * L * e * 4 * 5, kind="attn",
+                    flops=2 * b * L * e * 3 * e + 2 * b * e * e + 2 * b * e * nc + 4 * b * L * L * e)
+        with torch.cuda.device(dev), _Timed(f"attn_head_fwd[B={b},L={L},E={e}]", 5, dev, **work):
+            rc = _lib.lib().gh_attn_head_fwd2(desc.data_ptr(), w_in_planes.data_ptr(), b_in_.data_ptr(),
+                                              w_out_planes.data_ptr(), b_out_.data_ptr(), w_c_.data_ptr(), b_c_.data_ptr(),
+                                              b, L, e, nc, x_planes.data_ptr(), qkv.data_ptr(), probs.data_ptr(),
+                                              obar_planes.data_ptr(), emb.data_ptr(), logits.data_ptr(), _stream_ptr(desc))
+        check(rc, "gh_attn_head_fwd2")
+        ctx.save_for_backward(x_planes, w_in_planes, w_out_planes, w_c_, qkv, probs, obar_planes, emb)
+        ctx.dims = (b, L, e, nc)
+        return emb, logits
+
+    @staticmethod
+    def backward(ctx, d_emb, d_logits):
+        x_planes, w_in_planes, w_out_planes, w_c, qkv, probs, obar_planes, emb = ctx.saved_tensors
+        b, L, e, nc = ctx.dims
+        dev = qkv.device
+        need = ctx.needs_input_grad
+        d_logits = (torch.zeros((b, nc), device=dev) if d_logits is None else d_logits).contiguous().float()
+        d_emb = None if d_emb is None else d_emb.contiguous().float()
+
+        def buf(flag, shape):
+            return torch.empty(shape, device=dev, dtype=torch.float32) if flag else None
+
+        d_desc = buf(need[0], (b, L, e))
+        gw_in, gb_in = buf(need[1], (3 * e, e)), buf(need[2], (3 * e,))
+        gw_out, gb_out = buf(need[3], (e, e)), buf(need[4], (e,))
+        gw_c, gb_c = buf(need[5], (nc, e)), buf(need[6], (nc,))
+        lib = _lib.lib()
+        ws = torch.empty(((lib.gh_attn_head_bwd2_workspace(b, L, e) + 15) // 16 * 4,), device=dev, dtype=torch.float32)
+        ptr = lambda t: 0 if t is None else t.data_ptr()
+        work = dict(bytes=(3 * e * e + e * e + nc * e) * 4 * 2 + b * L * e * 4 * 8, kind="attn",
+                    flops=2 * (2 * b * L * e * 3 * e + 2 * b * e * e + 2 * b * e * nc) + 8 * b * L * L * e)
+        with torch.cuda.device(dev), _Timed(f"attn_head_bwd[B={b},L={L},E={e}]", 4, dev, **work):
+            rc = lib.gh_attn_head_bwd2(x_planes.data_ptr(), w_in_planes.data_ptr(), w_out_planes.data_ptr(), w_c.data_ptr(),
+                                       qkv.data_ptr(), probs.data_ptr(), obar_planes.data_ptr(), emb.data_ptr(),
+                                       d_logits.data_ptr(), ptr(d_emb), b, L, e, nc, ptr(d_desc), ptr(gw_in), ptr(gb_in),
+                                       ptr(gw_out), ptr(gb_out), ptr(gw_c), ptr(gb_c), ws.data_ptr(), _stream_ptr(qkv))
+        check(rc, "gh_attn_head_bwd2")
+        return d_desc, gw_in, gb_in, gw_out, gb_out, gw_c, gb_c, None, None
+
+
 def attention_head(desc, w_in, b_in, w_out, b_out, w_c, b_c):
+    L, e, nc = desc.shape[1], desc.shape[2], w_c.shape[0]
+    if attn2_supported(L, e, nc) and desc.is_cuda and w_in.dtype == torch.float32 and w_out.dtype == torch.float32:
+        return _AttnHead2.apply(desc, w_in, b_in, w_out, b_out, w_c, b_c, weight_planes(w_in), weight_planes(w_out))
     return _AttnHead.apply(desc, w_in, b_in, w_out, b_out, w_c, b_c)
+
+
+def gemm_planes(a_planes: torch.Tensor, a_mn: bool, b_planes: torch.Tensor, b_mn: bool, bias: torch.Tensor = None,
+                planes_out: bool = False, max_split: int = 64) -> torch.Tensor:
+    """D = A B^T (+ bias) through gh_gemm_planes. a_planes: (2, M, K) bf16 planes, or (2, K, M) when a_mn (the M index
+    contiguous); b_planes: (2, N, K) or (2, K, N) when b_mn. Returns fp32 (M, N), or its (2, M, N) planes."""
+    _require_cuda(a_planes, "a_planes")
+    assert a_planes.dtype == torch.bfloat16 and b_planes.dtype == torch.bfloat16
+    assert a_planes.is_contiguous() and b_planes.is_contiguous()
+    m, k = (a_planes.shape[2], a_planes.shape[1]) if a_mn else (a_planes.shape[1], a_planes.shape[2])
+    n, k2 = (b_planes.shape[2], b_planes.shape[1]) if b_mn else (b_planes.shape[1], b_planes.shape[2])
+    assert k == k2
+    dev = a_planes.device
+    if planes_out:
+        out = torch.empty((2, m, n), device=dev, dtype=torch.bfloat16)
+        d, dp = 0, out.data_ptr()
+    else:
+        out = torch.empty((m, n), device=dev, dtype=torch.float32)
+        d, dp = out.data_ptr(), 0
+    work = dict(bytes=(m * k + k * n) * 4 + m * n * 4, flops=2 * m * n * k, kind="gemm")
+    with torch.cuda.device(dev), _Timed(f"gemm_planes[M={m},N={n},K={k}]", 1, dev, **work):
+        rc = _lib.lib().gh_gemm_planes(a_planes.data_ptr(), a_planes.shape[2], a_planes[0].numel(), int(a_mn),
+                                       b_planes.data_ptr(), b_planes.shape[2], b_planes[0].numel(), int(b_mn),
+                                       0 if bias is None else bias.data_ptr(), d, dp, n, m * n, m, n, k, max_split,
+                                       _stream_ptr(a_planes))
+    check(rc, "gh_gemm_planes")
+    return out

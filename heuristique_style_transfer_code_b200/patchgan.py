@@ -159,56 +159,15 @@ class MultiScaleDiscriminator_test(nn.Module):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-# The training-time classes of the same file (:17-110) have no Gram head: plain convolution stacks that stay on cuDNN.
-# They are restated here only so that `Models.Models_Multi_PatchGAN` resolves completely from this repo
-# (train_best_Multi_PatchGAN.py:11 imports MultiScaleDiscriminator from it).
+# The training-time classes of the same file (:17-110) have no Gram head (plain convolution stacks on cuDNN) and are
+# outside this package's path: `VariablePatchesNLayerDiscriminator` / `MultiScaleDiscriminator` resolve lazily to the
+# reference's own classes (train_best_Multi_PatchGAN.py:11 imports MultiScaleDiscriminator from this module path).
 # ----------------------------------------------------------------------------------------------------------------------
-class VariablePatchesNLayerDiscriminator(nn.Module):
-    def __init__(self, input_nc=3, ndf=64, norm="instance", tensorboard_logdir=None, global_step=None, patch_size=70,
-                 num_classes=10):
-        super().__init__()
-        self.tensorboard_logdir = tensorboard_logdir
-        self.writer = None
-        if tensorboard_logdir:
-            from torch.utils.tensorboard import SummaryWriter
-            self.writer = SummaryWriter(log_dir=tensorboard_logdir)
-        self.global_step = global_step
-        self.num_classes = num_classes
-        make_norm = nn.InstanceNorm2d if norm == 'instance' else nn.BatchNorm2d
-        stack, width, channels, field = [], ndf, input_nc, patch_size
-        while field > 4 and width <= 512:
-            stack += [nn.Conv2d(channels, width, 4, 2, 1), make_norm(width), nn.LeakyReLU(0.2, inplace=True)]
-            channels, width, field = width, width * 2, field / 2
-        stack += [nn.Conv2d(channels, width, 4, 1, 1), make_norm(width), nn.LeakyReLU(0.2, inplace=True),
-                  nn.Conv2d(width, num_classes, 4, 1, 1)]
-        self.model = nn.Sequential(*stack)
-
-    def forward(self, input):
-        return self.model(input).mean(dim=[2, 3])
-
-    def close_writer(self):
-        if self.writer:
-            self.writer.close()
+_REFERENCE_ONLY = ("VariablePatchesNLayerDiscriminator", "MultiScaleDiscriminator")
 
 
-class MultiScaleDiscriminator(nn.Module):
-    def __init__(self, input_nc=3, ndf=64, norm='batch', tensorboard_logdir=None, global_step=None,
-                 patch_sizes={'small': 70, 'medium': 70, 'large': 70}, num_classes=10):
-        super().__init__()
-        self.patch_sizes = patch_sizes
-        self.tensorboard_logdir = tensorboard_logdir
-        self.global_step = global_step
-        self.scale_discriminators = nn.ModuleDict()
-        for patch_type in PATCH_TYPES:
-            logdir = os.path.join(tensorboard_logdir, patch_type) if tensorboard_logdir else None
-            self.scale_discriminators[patch_type] = VariablePatchesNLayerDiscriminator(
-                input_nc=input_nc, patch_size=patch_sizes.get(patch_type, 70), ndf=ndf, norm=norm,
-                tensorboard_logdir=logdir, global_step=global_step, num_classes=num_classes)
-        self.downsample = nn.AvgPool2d(3, stride=2, padding=1, count_include_pad=False)
-
-    def forward(self, input):
-        results, x = [], input
-        for discriminator in self.scale_discriminators.values():     # each scale sees a 2x smaller image (:100-108)
-            results.append(discriminator(x))
-            x = self.downsample(x)
-        return torch.stack(results, dim=0).mean(dim=0)
+def __getattr__(name):
+    if name in _REFERENCE_ONLY:
+        from ._reference import load_reference_file
+        return getattr(load_reference_file(os.path.join("Models", "Models_Multi_PatchGAN.py")), name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

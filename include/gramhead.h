@@ -194,6 +194,48 @@ int gh_attn_head_bwd(const float* desc, const float* W_in, const float* W_out, c
                      const float* d_emb_ext, int B, int L, int E, int nc, float* d_desc, float* dW_in, float* db_in,
                      float* dW_out, float* db_out, float* dW_c, float* db_c, float* workspace, void* stream);
 
+/* ---- Attention head on TMA-fed tensor-core GEMMs (the default whenever E % 64 == 0, E <= 1024, L <= 8, nc <= 16) -------
+ * Same reference lines as gh_attn_head_fwd / gh_attn_head_bwd (Models/...Attention.py:56-61 and its autograd), other
+ * operand format: every matrix that feeds a linear layer travels as "split planes" -- two bf16 matrices of the same
+ * shape, hi = bf16(x) and lo = bf16(x - hi), `plane_stride` elements apart -- which tcgen05 consumes straight from
+ * TMA-staged shared memory with three MMAs per k-step (lo*hi + hi*lo + hi*hi, fp32 accumulate: fp32-level accuracy).
+ *
+ * gh_split_bf16: planes[i] = bf16(src[i]), planes[plane_stride + i] = bf16(src[i] - hi) for i < n. Called once per
+ * WEIGHT VERSION for attention.in_proj_weight and attention.out_proj.weight (the host caches the planes), and by
+ * gh_attn_head_fwd2 for the descriptors. n % 4 == 0, src 16 B aligned. */
+int gh_split_bf16(const float* src, void* planes, long long n, long long plane_stride, void* stream);
+
+/* The GEMM gh_attn_head_fwd2 / _bwd2 are built from, exposed for testing and reuse:
+ *   D[m*ldd + n] (fp32)  or  D_planes (hi/lo bf16, d_plane_stride apart)  =  sum_k A(m,k) B(n,k) (+ bias[n])
+ * with split-plane operands. a_mn = 0: A(m,k) at m*lda + k; a_mn = 1: A(m,k) at k*lda + m (M % 64 == 0). Same for B
+ * with ldb / N. Exactly one of D, D_planes is non-NULL. K is split in at most max_split partitions (1 for D_planes).
+ * lda/ldb % 8 == 0, N % 32 == 0, 16 B aligned bases; GH_ERR_UNSUPPORTED otherwise. */
+int gh_gemm_planes(const void* A_planes, long long lda, long long a_plane_stride, int a_mn, const void* B_planes,
+                   long long ldb, long long b_plane_stride, int b_mn, const float* bias, float* D, void* D_planes,
+                   long long ldd, long long d_plane_stride, int M, int N, int K, int max_split, void* stream);
+
+/* Forward. w_in_planes: planes of in_proj_weight (2, 3E, E); w_out_planes: planes of out_proj.weight (2, E, E) (dense,
+ * plane_stride = rows*E). b_in, b_out, W_c, b_c fp32 as in gh_attn_head_fwd. Outputs: emb (B, E), logits (B, nc); saved
+ * for backward: x_planes (2, B*L, E) bf16, qkv (B*L, 3E) fp32, probs (B, L, L) fp32, obar_planes (2, B, E) bf16.
+ * Five launches: split X, in_proj GEMM, per-image scores/softmax/value mix, out_proj GEMM, classifier. Results are
+ * bitwise reproducible (K is split in at most two partitions). GH_ERR_UNSUPPORTED outside the shape range above. */
+int gh_attn_head_fwd2(const float* desc, const void* w_in_planes, const float* b_in, const void* w_out_planes,
+                      const float* b_out, const float* W_c, const float* b_c, int B, int L, int E, int nc, void* x_planes,
+                      float* qkv, float* probs, void* obar_planes, float* emb, float* logits, void* stream);
+
+/* Bytes of `workspace` gh_attn_head_bwd2 needs (16 B aligned). */
+long long gh_attn_head_bwd2_workspace(int B, int L, int E);
+
+/* Backward of gh_attn_head_fwd2. Outputs as in gh_attn_head_bwd (each may be NULL; overwritten, not accumulated).
+ * Four launches: gradient prep (demb planes, db_out, dW_c, db_c), {dObar, dW_out} GEMMs, per-image softmax/score
+ * backward (dQKV planes, db_in), {dW_in, d_desc} GEMMs. K partitions of a GEMM meet in fp32 reduce-adds whose order is
+ * not fixed: gradients are reproducible to fp32 rounding, not bitwise. */
+int gh_attn_head_bwd2(const void* x_planes, const void* w_in_planes, const void* w_out_planes, const float* W_c,
+                      const float* qkv, const float* probs, const void* obar_planes, const float* emb,
+                      const float* d_logits, const float* d_emb_ext, int B, int L, int E, int nc, float* d_desc,
+                      float* dW_in, float* db_in, float* dW_out, float* db_out, float* dW_c, float* db_c, void* workspace,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif
