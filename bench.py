@@ -11,13 +11,21 @@ the sm_100a head (3 pooled-Gram launches + attention/classifier). Multi-GPU: the
 
   value      images/s with the batch resident in HBM (154 MB of fp32 images per rank: larger than the 126 MB L2)
   e2e        same through the public call model(x_host): pinned host batch -> H2D -> forward -> logits+embeddings D2H
-  roofline   the library kernel that takes the most time inside the timed steps, measured live with CUDA events
-  cpu_baseline  the reference's CPU path (oracle/torch_port.py, op-for-op fp32 port) on this box's host cores, bounded sample
+  roofline   the HEAD kernel (Gram / attention) that takes the most time inside the timed steps, measured
+             live with CUDA events; backbone-side kernels of the library (max pool, stem staging) are listed under
+             `breakdown.kernels` only
+  cpu_baseline  the UNMODIFIED reference module (staged under baseline/_ref by tools/stage_reference.py and loaded by
+             file path; the oracle port when it is absent) on this box's host cores, bounded sample; next to it
+             `cpu_extra`: the reference head alone on captured stage activations and its training step at batch 8 with
+             anomaly detection as shipped (on) and off
+  reference_gpu  the same unmodified reference module on this B200 in fp32 (its own cuBLAS / cuDNN path): configs[1]
+             forward and configs[2] training step, backbone and head separated
   train      BASELINE.json configs[2]: full training step (forward + Gram backward + AdamW), global batch 512 sharded
-             over the N ranks with DDP/NCCL (strong scaling); reported as an extra object, not as `value`
+             over the N ranks with DDP/NCCL (strong scaling); reported as an extra object, not as `value`; its headline
+             scalars are repeated as the LAST keys of the line (train_strong_img_s, head_fwd_bwd_frac_of_bf16_peak, ...)
 
---impl reference times the reference's own CPU implementation of the same forward (the oracle port: /root/reference
-is not on the GPU box) with every host thread, on bounded samples of the same batch.
+--impl reference times the reference's own CPU implementation of the same forward (the unmodified reference class,
+kind "reference"; the oracle port, kind "port", only when baseline/_ref was not staged) with every host thread.
 """
 from __future__ import annotations
 
@@ -50,52 +58,53 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons of GPU `index`, sampled through NVML every 10 ms from a thread while the timed
+    region runs (an nvidia-smi subprocess needs longer to start than a 0.1 s region lasts, which left the multi-rank
+    runs of round 1 without samples)."""
+    REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40), ("sw_power_cap", 0x4))
 
-    def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
-
-    def __enter__(self):
+    def __init__(self, device):
+        self.rows, self.stop, self.thread, self.handle, self.nv = [], threading.Event(), None, None, None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
-            self.thread.start()
+            import pynvml
+            pynvml.nvmlInit()
+            p = torch.cuda.get_device_properties(device)
+            bus_id = f"{p.pci_domain_id:08x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+            self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus_id.encode())
+            self.nv = pynvml
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
         except Exception:
-            self.proc = None
-        return self
+            self.handle = None
 
     def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+        nv = self.nv
+        while not self.stop.is_set():
+            try:
+                self.rows.append((nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)))
+            except Exception:
+                pass
+            self.stop.wait(0.01)
+
+    def __enter__(self):
+        if self.handle is not None:
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        return self
 
     def __exit__(self, *exc):
-        if self.proc is not None:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
+        self.stop.set()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
         return False
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except Exception:
-                continue
-            for name, flag in zip(names, r[3:7]):
-                if flag.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+        if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        sm = [r[0] for r in self.rows]
+        reasons = sorted({name for _, mask in self.rows for name, bit in self.REASONS if mask & bit})
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm),
+                "how": "NVML, 10 ms period, during the timed region"}
 
 
 def timed_region(fn, steps, device, dist_mod):
@@ -112,6 +121,32 @@ def timed_region(fn, steps, device, dist_mod):
     return dist_mod.max_over_ranks(start.elapsed_time(end), device)
 
 
+HEAD_KINDS = ("gram_fwd", "gram_bwd", "attn")      # what the roofline object may name
+
+
+def head_totals(records, steps, peaks):
+    """Per-step time and algorithmic FLOPs of the head kernels (Gram forward: symmetric count C(C+1)HW; Gram backward:
+    dense 2 C^2 HW; attention: its GEMMs) and the fraction of the measured bf16 tensor peak they amount to."""
+    t = {"gram_fwd": 0.0, "gram_bwd": 0.0, "attn_fwd": 0.0, "attn_bwd": 0.0}
+    flops = 0.0
+    for name, work, s, e in records:
+        kind = work.get("kind")
+        if kind not in HEAD_KINDS:
+            continue
+        key = kind if kind != "attn" else ("attn_bwd" if name.startswith("attn_head_bwd") else "attn_fwd")
+        t[key] += s.elapsed_time(e) * 1e3
+        flops += work["flops"]
+    total_us = sum(t.values()) / steps
+    if total_us <= 0:
+        return None
+    tf = flops / steps / total_us / 1e6
+    return {"gram_fwd_us": round(t["gram_fwd"] / steps, 1), "gram_bwd_us": round(t["gram_bwd"] / steps, 1),
+            "attn_fwd_us": round(t["attn_fwd"] / steps, 1), "attn_bwd_us": round(t["attn_bwd"] / steps, 1),
+            "head_us": round(total_us, 1), "algorithmic_gflop_per_step": round(flops / steps / 1e9, 1),
+            "TFLOPs": round(tf, 1), "frac_of_bf16_peak_burst": round(tf / peaks["tensor_tflops_burst"], 4),
+            "frac_of_bf16_peak_sustained": round(tf / peaks["tensor_tflops"], 4)}
+
+
 def summarise_profile(records, peaks):
     """records: ops.PROFILE entries -> per-kernel averages and the roofline object of the dominant one."""
     agg = {}
@@ -124,9 +159,10 @@ def summarise_profile(records, peaks):
         ms = a["ms"] / a["n"]
         kernels[name] = dict(avg_us=round(ms * 1e3, 2), launches=a["n"], total_ms=round(a["ms"], 3),
                              GBps=round(a["work"]["bytes"] / ms / 1e6, 1), TFLOPs=round(a["work"]["flops"] / ms / 1e9, 1))
-    if not agg:
+    head = {k: v for k, v in agg.items() if v["work"].get("kind") in HEAD_KINDS}
+    if not head:
         return kernels, None
-    top = max(agg, key=lambda k: agg[k]["ms"])
+    top = max(head, key=lambda k: head[k]["ms"])
     a = agg[top]
     ms = a["ms"] / a["n"]
     t_hbm = a["work"]["bytes"] / (peaks["hbm_gbs"] * 1e9)
@@ -181,13 +217,69 @@ def patchgan_leg(device, peaks, steps, batch=256):
             "kernels": kernels, "roofline": roof}
 
 
-def cpu_reference_forward(batch, sample, steps, warmup, threads):
-    """The reference's CPU path (oracle port), eval + no_grad, on `sample` images of the synthetic batch."""
+def reference_classes():
+    """-> (train class, test class, kind): the UNMODIFIED reference classes, loaded by file path from the staged copy of
+    the reference tree (baseline/_ref travels to the GPU box; /root/reference does not); the oracle port only when no
+    copy of the reference is available."""
+    try:
+        from heuristique_style_transfer_code_b200._reference import load_reference_file
+        m = load_reference_file(os.path.join("Models", "Models_RESNET50_TRUNCATE_GRAM_with_Attention.py"))
+        return m.TruncatedResNet50, m.TruncatedResNet50_for_test, "reference"
+    except NotImplementedError:
+        from oracle.torch_port import PortModel
+
+        def train_cls(base, trunc, nc, g, device="cpu"):
+            return PortModel(base, trunc, nc, g, device=device, return_embeddings=False)
+
+        def test_cls(base, trunc, nc, g, device="cpu"):
+            return PortModel(base, trunc, nc, g, device=device, return_embeddings=True)
+        return train_cls, test_cls, "port"
+
+
+def reference_head(model, stages):
+    """The reference's head on given stage activations: its own op sequence (Models/...Attention.py:50-61) issued through
+    the reference module's gram_matrix / attention / classifier."""
+    F = torch.nn.functional
+    g = model.gram_matrix_size
+    grams = [F.adaptive_avg_pool2d(model.gram_matrix(a), (g, g)) for a in stages]
+    tokens = torch.stack(grams, dim=1).flatten(2).permute(1, 0, 2)
+    out, _ = model.attention(tokens, tokens, tokens)
+    emb = out.mean(dim=0)
+    return emb, model.classifier(emb)
+
+
+def capture_stages(model, x):
+    got = []
+    hooks = [blk.register_forward_hook(lambda m, i, o: got.append(o.detach()))
+             for blk in list(model.truncated_encoder.children())[4:]]
+    with torch.no_grad():
+        model(x)
+    for h in hooks:
+        h.remove()
+    return got
+
+
+def wall_time(fn, warmup, steps, sync=None):
+    times = []
+    for i in range(warmup + steps):
+        if sync:
+            sync()
+        t0 = time.perf_counter()
+        fn()
+        if sync:
+            sync()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return statistics.median(times)
+
+
+def cpu_reference_forward(sample, steps, warmup, threads):
+    """The reference's CPU path, eval + no_grad, on `sample` images of the synthetic batch -> (images/s, s/step, kind)."""
     from torchvision import models
-    from oracle.torch_port import PortModel
+    _, test_cls, kind = reference_classes()
     torch.set_num_threads(threads)
     torch.manual_seed(0)
-    model = PortModel(models.resnet50(weights=None), TRUNC, NUM_CLASSES, GRAM_SIZE, device="cpu", return_embeddings=True)
+    model = test_cls(models.resnet50(weights=None), TRUNC, NUM_CLASSES, GRAM_SIZE, device="cpu")
     model.eval()
     torch.manual_seed(1)
     x = torch.randn(sample, 3, IMAGE, IMAGE)
@@ -199,7 +291,101 @@ def cpu_reference_forward(batch, sample, steps, warmup, threads):
             dt = time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)
-    return sample * len(times) / sum(times), sum(times) / len(times)
+    return sample * len(times) / sum(times), sum(times) / len(times), kind
+
+
+def cpu_extra_legs(threads):
+    """BASELINE.md section 4, items 3b / 3c on this box's host cores: the reference head alone on captured stage
+    activations (batch 8), and its training step at batch 8 (SGD momentum 0.9, the reference's optimizer) with
+    torch.autograd anomaly detection as the reference ships it (on, Models/...Attention.py:9) and off."""
+    from torchvision import models
+    train_cls, test_cls, kind = reference_classes()
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    model = test_cls(models.resnet50(weights=None), TRUNC, NUM_CLASSES, GRAM_SIZE, device="cpu").eval()
+    torch.manual_seed(1)
+    x = torch.randn(8, 3, IMAGE, IMAGE)
+    stages = capture_stages(model, x)
+    with torch.no_grad():
+        head_s = wall_time(lambda: reference_head(model, stages), 2, 8)
+        fwd_s = wall_time(lambda: model(x), 2, 6)
+    tm = train_cls(models.resnet50(weights=None), TRUNC, NUM_CLASSES, GRAM_SIZE, device="cpu").train()
+    opt = torch.optim.SGD(tm.parameters(), lr=1e-3, momentum=0.9)
+    y = torch.randint(0, NUM_CLASSES, (8,))
+
+    def step():
+        opt.zero_grad()
+        torch.nn.functional.cross_entropy(tm(x), y).backward()
+        opt.step()
+    out = {"kind": kind, "cores": threads, "batch": 8, "forward_images_per_s": round(8 / fwd_s, 2),
+           "head_only_ms": round(head_s * 1e3, 2), "head_only_images_per_s": round(8 / head_s, 1)}
+    prev = torch.is_anomaly_enabled()
+    try:
+        for flag, key in ((True, "train_step_anomaly_on_s"), (False, "train_step_anomaly_off_s")):
+            torch.autograd.set_detect_anomaly(flag)
+            out[key] = round(wall_time(step, 1, 4), 3)
+    finally:
+        torch.autograd.set_detect_anomaly(prev)
+    out["train_images_per_s_as_shipped"] = round(8 / out["train_step_anomaly_on_s"], 2)
+    return out
+
+
+def reference_gpu_legs(device, steps):
+    """the unmodified reference module on this B200 in fp32, its own cuBLAS / cuDNN path
+    (torch defaults: fp32 matmul without TF32, cuDNN convolutions with TF32 allowed): configs[1] forward at batch 256 and
+    configs[2] training step at batch 512 (AdamW), the cuDNN backbone and the reference's head timed separately."""
+    from torchvision import models
+    train_cls, test_cls, kind = reference_classes()
+    sync = lambda: torch.cuda.synchronize(device)
+    torch.manual_seed(0)
+    model = test_cls(models.resnet50(weights=None), TRUNC, NUM_CLASSES, GRAM_SIZE, device=device).to(device).eval()
+    torch.manual_seed(1)
+    x = torch.randn(256, 3, IMAGE, IMAGE, device=device)
+    stages = capture_stages(model, x)
+    enc = model.truncated_encoder
+    with torch.no_grad():
+        fwd = wall_time(lambda: model(x), 3, steps, sync)
+        backbone = wall_time(lambda: enc(x), 3, steps, sync)
+        head = wall_time(lambda: reference_head(model, stages), 3, steps, sync)
+    out = {"kind": kind, "dtype": "fp32 (torch defaults)",
+           "infer_batch256": {"images_per_s": round(256 / fwd, 1), "ms_per_step": round(fwd * 1e3, 3),
+                              "backbone_ms": round(backbone * 1e3, 3), "head_ms": round(head * 1e3, 3)}}
+    del model, stages, x
+    torch.cuda.empty_cache()
+    torch.manual_seed(0)
+    tm = train_cls(models.resnet50(weights=None), TRUNC, NUM_CLASSES, GRAM_SIZE, device=device).to(device).train()
+    opt = torch.optim.AdamW(tm.parameters(), lr=1e-3)
+    xt = torch.randn(512, 3, IMAGE, IMAGE, device=device)
+    yt = torch.randint(0, NUM_CLASSES, (512,), device=device)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        torch.nn.functional.cross_entropy(tm(xt), yt).backward()
+        opt.step()
+
+    def backbone_step():
+        tm.truncated_encoder(xt).sum().backward()
+    tstep = wall_time(step, 2, max(3, steps // 2), sync)
+    bstep = wall_time(backbone_step, 2, max(3, steps // 2), sync)
+    tm.zero_grad(set_to_none=True)
+    out["train_batch512"] = {"images_per_s": round(512 / tstep, 1), "ms_per_step": round(tstep * 1e3, 2),
+                             "backbone_fwd_bwd_ms": round(bstep * 1e3, 2),
+                             "head_fwd_bwd_and_optimizer_ms": round((tstep - bstep) * 1e3, 2),
+                             "anomaly_detection": "off (the reference switches it on at import; see cpu_extra)"}
+    del tm, opt, xt, yt
+    torch.cuda.empty_cache()
+    return out
+
+
+def reference_sample_size(steps, warmup, threads, budget_s=150.0):
+    """Images per CPU step: the largest of 256 (the whole batch) / 128 / 64 / 32 with which `warmup + steps` forwards stay
+    inside `budget_s`, from the rate of one probe forward of 32 images (the per-image cost grows with the batch on a CPU:
+    the (B, C, C) Gram intermediates leave the caches)."""
+    ips, _, _ = cpu_reference_forward(32, 1, 1, threads)
+    for sample in (256, 128, 64):
+        if (steps + warmup) * sample / (0.6 * ips) <= budget_s:
+            return sample
+    return 32
 
 
 def run_reference(args):
@@ -207,16 +393,20 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = 16
-    ips, sec = cpu_reference_forward(256, sample, args.steps, max(args.warmup, 1), cores)
+    sample = reference_sample_size(args.steps, max(args.warmup, 1), cores)
+    ips, sec, kind = cpu_reference_forward(sample, args.steps, max(args.warmup, 1), cores)
+    what = ("the UNMODIFIED reference class TruncatedResNet50_for_test, loaded by file path from baseline/_ref "
+            "(tools/stage_reference.py)") if kind == "reference" else \
+        "oracle/torch_port.py: the reference's op sequence (no staged copy of the reference on this box)"
     line = {"impl": "reference", "metric": "images/sec", "value": round(ips, 2), "unit": "images/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "CPU has no batch-256 budget: each step is a 16-image sample of the batch"},
-            "cpu_baseline": {"value": round(ips, 2), "unit": "images/s", "cores": cores, "kind": "port",
-                             "sample": f"{sample} images of the 256-image batch per step, {args.steps} steps, torch "
-                                       f"{torch.__version__} CPU fp32, {cores} threads (oracle/torch_port.py: the "
-                                       "reference's op sequence; /root/reference is not on this box)"},
+            "config": {"workload": WORKLOAD, "global_batch": sample, "per_gpu_batch": sample, "image": IMAGE,
+                       "truncate_layer": TRUNC, "gram_matrix_size": GRAM_SIZE, "num_classes": NUM_CLASSES,
+                       "note": f"each step is one eval/no_grad forward of {sample} images of the batch on the host cores"},
+            "cpu_baseline": {"value": round(ips, 2), "unit": "images/s", "cores": cores, "kind": kind,
+                             "sample": f"{sample} images per step, {args.steps} steps after {max(args.warmup, 1)} warm-ups, "
+                                       f"torch {torch.__version__} CPU fp32, {cores} threads; {what}"},
             "e2e": {"value": round(ips, 2), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(json.dumps(line))
@@ -256,7 +446,7 @@ def run_ours(args):
         infer_step()
     ops.PROFILE = []
     ops.LAUNCHES = 0
-    with ClockSampler(local) as clocks:
+    with ClockSampler(device) as clocks:
         ms = timed_region(infer_step, args.steps, device, D)
     records, ops.PROFILE = ops.PROFILE, None
     launches = ops.LAUNCHES
@@ -393,13 +583,26 @@ def run_ours(args):
         tms = timed_region(train_step, tsteps, device, D)
         trec, ops.PROFILE = ops.PROFILE, None
         tk, troof = summarise_profile(trec, peaks)
+        thead = head_totals(trec, tsteps, peaks)
         train = {"metric": "images/sec", "value": round(gb * tsteps / (tms / 1e3), 1), "unit": "images/s",
                  "ms_per_step": round(tms / tsteps, 2), "steps": tsteps, "scaling": "strong",
                  "config": {"workload": "configs[2]: full training step (forward + Gram/attention backward + cuDNN "
                                         "backward + AdamW), train-mode BN, CE loss", "global_batch": gb,
                             "per_gpu_batch": hi - lo, "optimizer": "AdamW(lr=1e-3)",
                             "parallelism": f"ddp{world}" if world > 1 else "single"},
-                 "kernels": tk, "roofline": troof}
+                 "kernels": tk, "roofline": troof, "head": thead}
+        if world == 1 and not args.skip_handoff:
+            # The same step with the opt-in bf16 channels_last backbone: the head then reads bf16 features
+            # (kind::f16 operands), half the HBM bytes of the default fp32 hand-off. Reported beside, never as, the default.
+            tmodel.set_backbone_mode("bf16_channels_last")
+            for _ in range(2):
+                train_step()
+            ops.PROFILE = []
+            bms = timed_region(train_step, tsteps, device, D)
+            brec, ops.PROFILE = ops.PROFILE, None
+            train["bf16_handoff"] = {"value": round(gb * tsteps / (bms / 1e3), 1), "unit": "images/s",
+                                     "ms_per_step": round(bms / tsteps, 2), "head": head_totals(brec, tsteps, peaks)}
+            tmodel.set_backbone_mode("channels_last")
         if world > 1:
             # The same step with the per-GPU batch held at the single-GPU size (weak scaling, global batch gb * world):
             # at 512 / world images per GPU the cuDNN encoder's train-mode kernels stop shrinking with the shard
@@ -415,19 +618,27 @@ def run_ours(args):
                                      "ms_per_step": round(wms / tsteps, 2), "global_batch": gb * world,
                                      "per_gpu_batch": gb, "steps": tsteps, "scaling": "weak"}
         del xt, yt, tmodel, ddp, opt
+        torch.cuda.empty_cache()
 
     if rank != 0:
         return
 
-    cpu_base = None
+    ref_gpu = None
+    if world == 1 and not args.skip_reference_gpu:
+        ref_gpu = reference_gpu_legs(device, max(3, args.steps // 4))
+
+    cpu_base, cpu_extra = None, None
     if world == 1 and not args.skip_cpu:
         D.restore_cpu_affinity()                  # the CPU baseline gets every host core, not only the GPU-local ones
         cores = os.cpu_count() or 1
-        sample = 16
-        ips, sec = cpu_reference_forward(B, sample, 6, 2, cores)
-        cpu_base = {"value": round(ips, 2), "unit": "images/s", "cores": cores, "kind": "port",
-                    "sample": f"{sample} images of the batch per step, 6 steps after 2 warm-ups ({sec:.2f} s/step), torch "
-                              f"{torch.__version__} CPU fp32 eval/no_grad, {cores} threads, oracle/torch_port.py"}
+        sample = 64
+        ips, sec, kind = cpu_reference_forward(sample, 5, 2, cores)
+        cpu_base = {"value": round(ips, 2), "unit": "images/s", "cores": cores, "kind": kind,
+                    "sample": f"{sample} images of the batch per step, 5 steps after 2 warm-ups ({sec:.2f} s/step), torch "
+                              f"{torch.__version__} CPU fp32 eval/no_grad, {cores} threads, "
+                              + ("unmodified reference class loaded from baseline/_ref" if kind == "reference"
+                                 else "oracle/torch_port.py")}
+        cpu_extra = cpu_extra_legs(cores)
 
     line = {"metric": "images/sec", "value": round(value, 1), "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
@@ -452,7 +663,30 @@ def run_ours(args):
                           "head_images_per_s": round(B / (head_ms / 1e3), 1), "kernels": kernels},
             "backbone_handoff": handoff,
             "patchgan_head": patchgan,
+            "cpu_extra": cpu_extra,
+            "reference_gpu": ref_gpu,
             "train": train}
+    # headline scalars repeated as the LAST keys, so that they survive a truncated tail of this (long) line
+    ihead = head_totals(records, args.steps, peaks)
+    line["infer_head_us"] = ihead["head_us"] if ihead else None
+    line["infer_attn_fwd_us"] = ihead["attn_fwd_us"] if ihead else None
+    if train is not None:
+        th = train.get("head") or {}
+        key = "train_strong_img_s" if world > 1 else "train_img_s"
+        line[key] = train["value"]
+        line["train_ms_per_step"] = train["ms_per_step"]
+        if "weak_scaling" in train:
+            line["train_weak_img_s"] = train["weak_scaling"]["value"]
+        line["train_attn_fwd_us"] = th.get("attn_fwd_us")
+        line["train_attn_bwd_us"] = th.get("attn_bwd_us")
+        line["train_head_fwd_bwd_us"] = th.get("head_us")
+        line["head_fwd_bwd_frac_of_bf16_peak"] = th.get("frac_of_bf16_peak_burst")
+        bh = (train.get("bf16_handoff") or {}).get("head") or {}
+        line["head_fwd_bwd_frac_of_bf16_peak_bf16_handoff"] = bh.get("frac_of_bf16_peak_burst")
+    if ref_gpu is not None:
+        line["reference_gpu_infer_img_s"] = ref_gpu["infer_batch256"]["images_per_s"]
+        line["reference_gpu_train_img_s"] = ref_gpu["train_batch512"]["images_per_s"]
+    line["e2e_img_s"] = round(e2e_value, 1)
     emit(json.dumps(line))
 
 
@@ -490,6 +724,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-handoff", action="store_true")
     ap.add_argument("--skip-patchgan", action="store_true")
+    ap.add_argument("--skip-reference-gpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

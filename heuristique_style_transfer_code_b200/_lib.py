@@ -44,6 +44,8 @@ _SIGNATURES = {
     "gh_patch_attn_fwd": (c_int, [_P] * 11 + [c_int] * 5 + [_P, _P, _P]),
     "gh_attn_head_bwd_workspace": (c_longlong, [c_int, c_int, c_int]),
     "gh_attn_head_bwd": (c_int, [_P] * 10 + [c_int] * 4 + [_P] * 8 + [_P]),
+    "gh_gram_mse_blocks": (c_int, [c_longlong]),
+    "gh_gram_mse": (c_int, [_P, _P, c_longlong, _P, _P, _P]),
     "gh_split_bf16": (c_int, [_P, _P, c_longlong, c_longlong, _P]),
     "gh_gemm_planes": (c_int, [_P, c_longlong, c_longlong, c_int, _P, c_longlong, c_longlong, c_int, _P, _P, _P,
                                 c_longlong, c_longlong, c_int, c_int, c_int, c_int, _P]),

@@ -12,19 +12,43 @@
 namespace gh {
 
 // ---------------------------------------------------------------------------------------------
-// Error reporting from device code. A bounded mbarrier wait that runs out of time records where
-// it happened and traps, so a protocol bug surfaces as a launch failure instead of a hung GPU.
+// Error reporting from device code. A bounded mbarrier wait that runs out of time records where it happened and
+// traps, so a protocol bug surfaces as a launch failure instead of a hung GPU. The record {code, blockIdx.x,
+// threadIdx.x, site tag} lives in MAPPED PINNED HOST memory (error_record_host(), below): after a trap the context is in
+// a sticky error state and no CUDA call could copy it back, but the host can still read its own memory.
 // ---------------------------------------------------------------------------------------------
-__device__ unsigned int g_dev_error[4];   // [0]=code, [1]=blockIdx.x, [2]=threadIdx.x, [3]=site tag
+__device__ unsigned int* g_dev_error_ptr = nullptr;   // device address of the mapped record; null until the library's
+                                                      // first launch on this device (error_record_host())
 
 __device__ __forceinline__ void dev_fail(unsigned int code, unsigned int site) {
-  if (atomicCAS(&g_dev_error[0], 0u, code) == 0u) {
-    g_dev_error[1] = blockIdx.x;
-    g_dev_error[2] = threadIdx.x;
-    g_dev_error[3] = site;
+  unsigned int* rec = g_dev_error_ptr;
+  if (rec != nullptr && atomicCAS_system(rec, 0u, code) == 0u) {
+    rec[1] = blockIdx.x;
+    rec[2] = threadIdx.x;
+    rec[3] = site;
     __threadfence_system();
   }
   __trap();
+}
+
+// Host side: the record of the current device, allocated and published to g_dev_error_ptr on first use.
+inline volatile unsigned int* error_record_host() {
+  static unsigned int* host_rec[64] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (host_rec[dev] == nullptr) {
+    unsigned int* h = nullptr;
+    unsigned int* d = nullptr;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&h), 4 * sizeof(unsigned int), cudaHostAllocMapped) != cudaSuccess) return nullptr;
+    h[0] = h[1] = h[2] = h[3] = 0u;
+    if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&d), h, 0) != cudaSuccess ||
+        cudaMemcpyToSymbol(g_dev_error_ptr, &d, sizeof(d)) != cudaSuccess) {
+      cudaFreeHost(h);
+      return nullptr;
+    }
+    host_rec[dev] = h;
+  }
+  return host_rec[dev];
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -118,6 +118,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = (int)cluster_id_x(), npairs = (int)cluster_nclusters_x();
+  // Every pair walks a CONTIGUOUS range of units: consecutive units then belong to the same image (nHT * nCB units per
+  // image), so the generators switch gradient tables -- and synchronise among themselves -- only when the image changes,
+  // and the two channel blocks of an x tile read the same F tiles back to back (the second time from L2).
+  const int u_begin = (int)(((long long)p.total_units * pair) / npairs);
+  const int u_end = (int)(((long long)p.total_units * (pair + 1)) / npairs);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmF);
@@ -158,7 +163,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
     if (elected) {
       uint32_t n = 0;
       const uint32_t tx_bytes = NHWC ? 2u * (uint32_t)(p.NT / 2) * kRowBytes : 2u * (uint32_t)na * kAtomBytesB;
-      for (int u = pair; u < p.total_units; u += npairs) {
+      for (int u = u_begin; u < u_end; ++u) {
         const GramBwdPairUnit w = gbp_decode(p, u);
         const int x0 = w.ht * p.NT + (int)rank * (p.NT / 2);
         for (int kc = 0; kc < p.nkc; ++kc, ++n) {
@@ -193,7 +198,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
       constexpr uint64_t kStageInc = kBpTileBytes >> 4, kAInc = 32u >> 4, kBInc = NHWC ? 32u >> 4 : kStepBytesB >> 4;
       const int full_chunks = p.C / (int)KC;
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
-      for (int u = pair; u < p.total_units; u += npairs, ++it) {
+      for (int u = u_begin; u < u_end; ++u, ++it) {
         const uint32_t ab = it & 1u, use = it >> 1;
         mbar_wait_cl(bar_tempty + 8 * ab, (use & 1u) ^ 1u, 200u + ab);
         tc_fence_after_sync();
@@ -228,7 +233,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
     const int q = warp & 3;                                 // TMEM lane quarter this warp may read
     const uint32_t my_store = store_smem + (uint32_t)(warp - 2) * (kBpStoreBufs * 4096u);
     uint32_t it = 0, buf = 0;
-    for (int u = pair; u < p.total_units; u += npairs, ++it) {
+    for (int u = u_begin; u < u_end; ++u, ++it) {
       const GramBwdPairUnit w = gbp_decode(p, u);
       const uint32_t ab = it & 1u, use = it >> 1;
       mbar_wait(bar_tfull + 8 * ab, use & 1u, 400u + ab);
@@ -319,17 +324,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
         table[gg + gall] = 0.f;
         table[kBpTableFloats + gg + gall] = 0.f;
       }
-      if (pair < p.total_units) {
-        fetch_table(gbp_decode(p, pair).b);
+      if (u_begin < u_end) {
+        fetch_table(gbp_decode(p, u_begin).b);
         publish_table(0);
       }
       named_bar_sync(1, kBpGenThreads);
     }
     int n0 = 0;                                             // sequence number of the unit's first K chunk
-    for (int u = pair; u < p.total_units; u += npairs, n0 += p.nkc) {
+    for (int u = u_begin; u < u_end; ++u, n0 += p.nkc) {
       const GramBwdPairUnit w = gbp_decode(p, u);
-      const bool has_next = u + npairs < p.total_units;
-      if (MODE == GRAM_POOL && has_next) fetch_table(gbp_decode(p, u + npairs).b);
+      // the table changes only when the next unit belongs to another image
+      const bool switch_table = MODE == GRAM_POOL && u + 1 < u_end && gbp_decode(p, u + 1).b != w.b;
+      if (switch_table) fetch_table(gbp_decode(p, u + 1).b);
       const int c = w.cb * 256 + (int)rank * 128 + (int)row;
       const bool row_ok = c < p.C;
       const float* srow = table + cur * kBpTableFloats + (row_ok ? (c >> p.kshift) * p.g : gg);
@@ -375,8 +381,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(fullA_leader + 8 * stage);
       }
-      if (MODE == GRAM_POOL) {
-        if (has_next) publish_table(cur ^ 1);               // last read one unit ago, before the barrier that ended it
+      if (switch_table) {
+        publish_table(cur ^ 1);                             // last read before the barrier of the previous switch
         named_bar_sync(1, kBpGenThreads);                   // every group sees the next table and is done with this one
         cur ^= 1;
       }
@@ -392,13 +398,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
   }
 }
 
-// x-tile plan: nHT tiles of NT (multiple of 32, 64 <= NT <= 256) covering HW with the least padded MMA work.
+// x-tile plan: nHT tiles of NT (64 <= NT <= 256) covering HW with the least padded MMA work. NT is a multiple of 32 (the
+// epilogue drains 32 columns at a time); a map that fits ONE tile may use a multiple of 16 (the MMA's N granularity):
+// the half-filled last chunk then lies beyond HW, where the TMA store clips it (HW = 196 -> NT = 208 instead of 224).
 inline void gbp_plan_tiles(int HW, int* NT, int* nHT) {
   int best_nt = 256, best_n = (HW + 255) / 256;
   long long best_cost = (long long)best_nt * best_n;
   const int n0 = (HW + 255) / 256;
   for (int n = n0; n <= n0 + 3; ++n) {
     int nt = ((HW + n - 1) / n + 31) / 32 * 32;
+    if (n == 1) nt = (HW + 15) / 16 * 16;
     if (nt < 64) nt = 64;
     if (nt > 256) continue;
     const long long cost = (long long)nt * n;

@@ -15,6 +15,7 @@
 #include "transpose.cuh"
 #include "patchgan.cuh"
 #include "pool.cuh"
+#include "style_loss.cuh"
 #include <string>
 
 namespace gh {
@@ -27,6 +28,7 @@ static int sm_count_cached() {
     int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
     cached[dev] = n;
+    error_record_host();       // every launcher passes here first: the device-side error record exists before any kernel runs
   }
   return cached[dev];
 }
@@ -518,11 +520,11 @@ int gh_set_option(const char* name, int value) {
 
 int gh_last_device_error(unsigned int* out4) {
   if (!out4) return GH_ERR_BAD_ARG;
-  cudaError_t e = cudaMemcpyFromSymbol(out4, g_dev_error, sizeof(unsigned int) * 4);
-  if (e != cudaSuccess) return (int)e;
-  unsigned int z[4] = {0, 0, 0, 0};
-  e = cudaMemcpyToSymbol(g_dev_error, z, sizeof(z));
-  return (int)e;
+  volatile unsigned int* rec = error_record_host();
+  if (!rec) return GH_ERR_UNSUPPORTED;
+  for (int i = 0; i < 4; ++i) out4[i] = rec[i];
+  for (int i = 3; i >= 0; --i) rec[i] = 0u;
+  return 0;
 }
 
 int gh_gram_pool_fwd(const void* F, int f_dtype, long long img_stride, long long row_stride, long long x_stride, int B,
@@ -674,6 +676,22 @@ int gh_stem_space_to_depth(const float* x, long long img_stride, long long c_str
   const int grid = (int)(want < cap ? want : cap);
   if (z_dtype == GH_DTYPE_F32) stem_space_to_depth_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
   else stem_space_to_depth_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  return (int)cudaGetLastError();
+}
+
+int gh_gram_mse_blocks(long long n) {
+  if (n <= 0) return 0;
+  long long blocks = (n / 4 + kMseThreads - 1) / kMseThreads;
+  const long long cap = (long long)sm_count_cached() * 4 < kMseMaxBlocks ? (long long)sm_count_cached() * 4 : kMseMaxBlocks;
+  if (blocks > cap) blocks = cap;
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+
+int gh_gram_mse(const float* G, const float* G_target, long long n, float* dG, float* partial, void* stream) {
+  if (!G || !G_target || !dG || !partial || n <= 0) return GH_ERR_BAD_ARG;
+  if (n % 4 != 0 || ((uintptr_t)G | (uintptr_t)G_target | (uintptr_t)dG) % 16 != 0) return GH_ERR_UNSUPPORTED;
+  gram_mse_kernel<<<gh_gram_mse_blocks(n), kMseThreads, 0, (cudaStream_t)stream>>>(G, G_target, dG, partial, n / 4,
+                                                                                   1.0f / (float)n);
   return (int)cudaGetLastError();
 }
 

@@ -378,7 +378,10 @@ inline void tg_plan(TgSpec* specs, int n, int npairs) {
         for (int ks = 1; ks <= nkb && ks <= (s.max_split > 0 ? s.max_split : 1); ++ks) {
           if (ks > 1 && nkb / ks < 2) break;
           const double cost = (double)((nkb + ks - 1) / ks) * tn / 256.0;
-          if (cost <= U && (cost > pick_cost + 1e-9)) { pick_cost = cost; pick_tn = tn; pick_ks = ks; }
+          // equal length: the unsplit (narrower) tiling wins -- no zeroed output, no reduce-add traffic
+          if (cost <= U && (cost > pick_cost + 1e-9 || (cost > pick_cost - 1e-9 && ks < pick_ks))) {
+            pick_cost = cost; pick_tn = tn; pick_ks = ks;
+          }
           if (cost < fallback_cost) { fallback_cost = cost; fb_tn = tn; fb_ks = ks; }
         }
       }

@@ -63,8 +63,11 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int, torch.d
     device = torch.device(f"cuda:{local}") if use_cuda else torch.device("cpu")
     if use_cuda:
         torch.cuda.set_device(device)
+        # "auto": only with several ranks per box, where the scheduler may otherwise place a rank on the socket far from
+        # its GPU; a single rank keeps every core (its launch thread, the pinned-buffer copies of HostCollector and the
+        # sampler processes then never compete for a narrowed CPU set).
         want = os.environ.get("GRAMHEAD_CPU_AFFINITY", "auto")
-        if want in ("1", "auto"):
+        if want == "1" or (want == "auto" and world > 1):
             bind_to_gpu_cpus(device)
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")

@@ -15,6 +15,8 @@ import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+from . import ops
 from torch.utils.data import Subset
 
 
@@ -124,6 +126,9 @@ def cuda_prefetch(batches, device, reuse_buffers=False):
             yield tuple(t.to(device) if torch.is_tensor(t) else t for t in batch)
         return
     copy_stream = _copy_stream(device)
+    # Uploads of this generator start after everything already queued on the consumer's stream: buffers of an earlier
+    # generator that the caching allocator hands back to the copy stream may still be read by that queued work.
+    copy_stream.wait_stream(torch.cuda.current_stream(device))
     slots = [None, None]              # per slot: list of device buffers (one per tensor position of the batch)
     consumed = [None, None]           # per slot: event on the consumer's stream after its last use of the slot
     count = 0
@@ -161,23 +166,32 @@ def cuda_prefetch(batches, device, reuse_buffers=False):
         pending = upload(next(it))
     except StopIteration:
         return
-    while pending is not None:
-        current, done, slot = pending
-        try:
-            pending = upload(next(it))          # queued before the consumer touches `current`: overlaps its compute
-        except StopIteration:
-            pending = None
-        main = torch.cuda.current_stream(device)
-        main.wait_event(done)
-        if not reuse_buffers:
-            for t in current:
-                if torch.is_tensor(t):
-                    t.record_stream(main)
-        yield current
-        if reuse_buffers:                       # the consumer has queued everything that reads `current`
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream(device))
-            consumed[slot] = ev
+    try:
+        while pending is not None:
+            current, done, slot = pending
+            try:
+                pending = upload(next(it))          # queued before the consumer touches `current`: overlaps its compute
+            except StopIteration:
+                pending = None
+            main = torch.cuda.current_stream(device)
+            main.wait_event(done)
+            if not reuse_buffers:
+                for t in current:
+                    if torch.is_tensor(t):
+                        t.record_stream(main)
+            yield current
+            if reuse_buffers:                       # the consumer has queued everything that reads `current`
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(device))
+                consumed[slot] = ev
+    finally:
+        if reuse_buffers:
+            # the staging buffers were allocated on the copy stream but read on the consumer's: tell the allocator, so that
+            # they are not handed out again before the consumer's queued work is done with them
+            main = torch.cuda.current_stream(device)
+            for bufs in slots:
+                for buf in (bufs or {}).values():
+                    buf.record_stream(main)
 
 
 class HostCollector:
@@ -360,7 +374,11 @@ class _StyleIteration:
         self.graph = None
 
     def _step(self):
-        loss = self.mse(self.model.gram_matrix(self.encoder(self.noise)), self.target)
+        features = self.encoder(self.noise)
+        if features.is_cuda:       # Gram forward, fused loss + dG pass, Gram backward (ops.gram_mse_loss; reference :286-295)
+            loss = ops.gram_mse_loss(features, self.target)
+        else:
+            loss = self.mse(self.model.gram_matrix(features), self.target)
         loss.backward()
         self.optimizer.step()
         return loss

@@ -359,6 +359,43 @@ def gram_matrix(x: torch.Tensor) -> torch.Tensor:
     return _GramDense.apply(x)
 
 
+class _GramMSE(torch.autograd.Function):
+    """mse_loss(gram_matrix(x), target) as one differentiable op (style transfer, reference functions/...:286-301):
+    dense Gram forward, one fused pass for the loss and d loss / d G (gh_gram_mse), dense Gram backward."""
+
+    @staticmethod
+    def forward(ctx, x, target):
+        ctx.meta = (tuple(x.shape), x.dtype, is_channels_last(x) and not nhwc_native(x))
+        if ctx.meta[2]:
+            x = nhwc_to_nchw(x)
+        gram = gram_dense_fwd(x)
+        target = target.detach().contiguous().float()
+        if target.shape != gram.shape:
+            raise GramHeadError(f"gramhead: target Gram {tuple(target.shape)} does not match {tuple(gram.shape)}")
+        n = gram.numel()
+        lib = _lib.lib()
+        d_gram = torch.empty_like(gram)
+        partial = torch.empty((lib.gh_gram_mse_blocks(n),), device=gram.device, dtype=torch.float32)
+        with torch.cuda.device(x.device), _Timed(f"gram_mse[n={n}]", 1, x.device, bytes=3 * n * 4, flops=3 * n, kind="style"):
+            rc = lib.gh_gram_mse(gram.data_ptr(), target.data_ptr(), n, d_gram.data_ptr(), partial.data_ptr(), _stream_ptr(x))
+        check(rc, "gh_gram_mse")
+        ctx.save_for_backward(x, d_gram)
+        return partial.sum()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, d_gram = ctx.saved_tensors
+        df = gram_dense_bwd(x, d_gram * grad_out)            # grad_out is 1 in the style-transfer loop (loss.backward())
+        if df.dim() == 4:
+            return df.to(ctx.meta[1]), None
+        return grad_like_activation(df, *ctx.meta), None
+
+
+def gram_mse_loss(x: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """mean((gram_matrix(x) - target)^2): x (B, C, H, W) activations, target (B, C, C)."""
+    return _GramMSE.apply(x, target)
+
+
 class _StyleDescriptor(torch.autograd.Function):
     """L stage activations -> (B, L, g*g) pooled-Gram descriptors (the attention's input, batch-major)."""
 

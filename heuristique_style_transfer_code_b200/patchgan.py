@@ -20,9 +20,14 @@ norm and the softmax over layers all propagate it), so here the forward runs onc
 (B, ndf) / (B, nc) results, and -- only if they hold a NaN -- runs again layer by layer with the reference's checks,
 messages and replacements. Clean inputs pay one tiny check instead of ~20 synchronisations.
 
-The head is inference-only, like its callers (every call site in functions_Multi_PatchGAN.py that uses these classes
-for classification is under torch.no_grad(): :164, :200, :464): a forward that would need gradients through the head
-raises GramHeadError instead of silently returning tensors without history.
+Gradients. The kernels implement the forward only: the classification / evaluation / camera call sites
+(functions_Multi_PatchGAN.py:164, :200, :464) run under torch.no_grad(). One upstream mode needs gradients THROUGH the
+head down to the input image -- `style_transfer_patches` (functions_Multi_PatchGAN.py:272-287: `model(noise_image)` with
+noise_image.requires_grad, then `loss.backward()`), a mode outside this package's path. So that it
+keeps working where the reference works, a forward that needs autograd history is handed to the reference's OWN forward
+(Models/Models_Multi_PatchGAN.py:177-256, executed on this module's parameters; loaded by _reference.py) instead of the
+kernels; when no copy of the reference is available it raises GramHeadError rather than returning tensors without
+history.
 """
 from __future__ import annotations
 
@@ -76,10 +81,19 @@ class VariablePatchesNLayerDiscriminator_test(nn.Module):
         self.feature_projection = nn.Linear(gram_matrix_dim * gram_matrix_dim, ndf)        # :175
 
     # -- the head ------------------------------------------------------------------------------------------------------
-    def _check_inference(self, x):
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise GramHeadError("gramhead: the Multi-PatchGAN Gram head is inference-only; call it under "
-                                "torch.no_grad() (as evaluate_model_test / evaluate_classification / run_camera do)")
+    def _needs_autograd(self, x):
+        return torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+
+    def _reference_forward(self, x):
+        """The reference's own forward on this module's parameters (differentiable; see the module docstring)."""
+        from ._reference import load_reference_file
+        try:
+            ref = load_reference_file(os.path.join("Models", "Models_Multi_PatchGAN.py"))
+        except NotImplementedError as exc:
+            raise GramHeadError("gramhead: the Multi-PatchGAN Gram head kernels are inference-only and no copy of the "
+                                "reference is available for a forward that needs gradients: call the model under "
+                                "torch.no_grad(), or " + str(exc)) from exc
+        return ref.VariablePatchesNLayerDiscriminator_test.forward(self, x)
 
     def _forward(self, x, careful: bool):
         maps, k = [], 0
@@ -115,7 +129,8 @@ class VariablePatchesNLayerDiscriminator_test(nn.Module):
         assert input.ndim == 4, f"Input must be NCHW, got {input.shape}"
         if not input.is_cuda:
             raise GramHeadError(f"gramhead: input must be a CUDA tensor (got {input.device}); the head has no CPU path")
-        self._check_inference(input)
+        if self._needs_autograd(input):
+            return self._reference_forward(input)
         with torch.no_grad():
             emb, out, norms = self._forward(input, careful=False)
             if bool(torch.isnan(emb).any() | torch.isnan(out).any()):

@@ -40,8 +40,10 @@ int gh_sm_count(void);
  * layers, 0 = fp32 FMA kernels; default 1). Unknown name or value outside the allowed set: GH_ERR_BAD_ARG. */
 int gh_set_option(const char* name, int value);
 
-/* Copies the device-side error record {code, blockIdx.x, threadIdx.x, site} to host memory `out4` and clears it.
- * code 1 = an mbarrier wait inside a kernel ran out of time (the kernel traps instead of hanging). Synchronises. */
+/* Reads and clears the error record {code, blockIdx.x, threadIdx.x, site} of the current device into host memory `out4`.
+ * code 1 = an mbarrier wait inside a kernel ran out of time (the kernel then traps instead of hanging the GPU). The
+ * record lives in mapped pinned host memory, so it can be read after the trap, when the CUDA context itself only
+ * returns errors; no CUDA call is made once the record exists. GH_ERR_UNSUPPORTED when it could not be allocated. */
 int gh_last_device_error(unsigned int* out4);
 
 /* Pooled Gram, forward.  Replaces, for one encoder stage l of L,
@@ -193,6 +195,14 @@ int gh_attn_head_bwd(const float* desc, const float* W_in, const float* W_out, c
                      const float* probs, const float* obar, const float* emb, const float* d_logits,
                      const float* d_emb_ext, int B, int L, int E, int nc, float* d_desc, float* dW_in, float* db_in,
                      float* dW_out, float* db_out, float* dW_c, float* db_c, float* workspace, void* stream);
+
+/* Style-transfer loss on the dense Gram. Replaces `loss = mse_loss(noise_gram, original_gram)` and the
+ * element-wise part of `loss.backward()` (functions/functions_RESNET50_Truncate_Gram_Attention.py:291-295):
+ *   partial[i] = sum over block i's elements of (G - G_target)^2 / n     (loss = sum_i partial[i], i < gh_gram_mse_blocks(n))
+ *   dG         = 2 (G - G_target) / n                                      (d loss / d G; feed it to gh_gram_dense_bwd)
+ * G, G_target, dG: n = B*C*C fp32 elements, 16 B aligned, n % 4 == 0. */
+int gh_gram_mse_blocks(long long n);
+int gh_gram_mse(const float* G, const float* G_target, long long n, float* dG, float* partial, void* stream);
 
 /* ---- Attention head on TMA-fed tensor-core GEMMs (the default whenever E % 64 == 0, E <= 1024, L <= 8, nc <= 16) -------
  * Same reference lines as gh_attn_head_fwd / gh_attn_head_bwd (Models/...Attention.py:56-61 and its autograd), other

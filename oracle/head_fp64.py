@@ -170,6 +170,19 @@ def gram_dense_backward(features: np.ndarray, d_gram: np.ndarray) -> np.ndarray:
     return (np.einsum("bcd,bdk->bck", dg + dg.transpose(0, 2, 1), f) / f.shape[2]).reshape(shape)
 
 
+def style_loss_and_grad(features: np.ndarray, target_gram: np.ndarray):
+    """Style-transfer objective of one layer (functions/functions_RESNET50_Truncate_Gram_Attention.py:286-295:
+    `noise_gram = model.gram_matrix(noise_features); loss = mse_loss(noise_gram, original_gram); loss.backward()`):
+    loss = mean over all B*C*C entries of (G - G*)^2 with G = F F^T / HW (Models/...:26-30), and the gradient that reaches
+    the activations, dF = (dG + dG^T) F / HW with dG = 2 (G - G*) / (B C C). features (B, C, HW), target (B, C, C).
+    -> (loss, dF (B, C, HW))"""
+    f = np.asarray(features, np.float64)
+    diff = gram(f) - np.asarray(target_gram, np.float64)
+    loss = float(np.mean(diff * diff))
+    d_gram = 2.0 * diff / diff.size
+    return loss, gram_dense_backward(f, d_gram)
+
+
 def head_backward(features: Sequence[np.ndarray], g: int, params: Dict[str, np.ndarray], cache: Dict[str, np.ndarray],
                   d_logits: np.ndarray, d_emb_ext: Optional[np.ndarray] = None) -> Dict[str, object]:
     grads = attention_backward(cache, params, d_logits, d_emb_ext)

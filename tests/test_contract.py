@@ -257,3 +257,48 @@ def test_host_collector_and_buffer_reusing_prefetch_on_cpu():
     batches = [(torch.full((2, 3), float(i)), torch.tensor([i, i]), "meta") for i in range(4)]
     got = list(cuda_prefetch(iter(batches), "cpu", reuse_buffers=True))
     assert len(got) == 4 and all(torch.equal(g[0], b[0]) and g[2] == "meta" for g, b in zip(got, batches))
+
+
+def test_checkpoint_converters_produce_what_load_model_loads(tmp_path):
+    """a torchvision ResNet50 state_dict and a three-section checkpoint match nothing in
+    load_model (reference behaviour, preserved); their converted bare-encoder form fills every encoder tensor."""
+    import torch
+    from torchvision import models
+    from heuristique_style_transfer_code_b200 import TruncatedResNet50, checkpoints
+    from heuristique_style_transfer_code_b200.functions import load_model, save_model_weights
+
+    torch.manual_seed(3)
+    donor = models.resnet50(weights=None)
+    model = TruncatedResNet50(models.resnet50(weights=None), 7, 4, 8, device="cpu")
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    n_enc = sum(1 for k in before if k.startswith("truncated_encoder."))
+
+    # (1) plain torchvision names: load_model "succeeds" and loads nothing
+    plain = tmp_path / "resnet50.pth"
+    torch.save(donor.state_dict(), plain)
+    assert checkpoints.coverage(model, donor.state_dict()) == {"matched": 0, "encoder": n_enc,
+                                                               "dropped": len(donor.state_dict()) - 2}
+    load_model(model, str(plain), "cpu")
+    assert all(torch.equal(v, before[k]) for k, v in model.state_dict().items())
+
+    # (2) converted: every encoder tensor now comes from the donor
+    bare = tmp_path / "bare.pth"
+    assert checkpoints.convert_file(str(plain), str(bare)) > 0
+    converted = torch.load(bare)
+    cov = checkpoints.coverage(model, converted)
+    assert cov["matched"] == n_enc                      # layer4 tensors are converted too and dropped by load_model
+    load_model(model, str(bare), "cpu")
+    sd = model.state_dict()
+    assert torch.equal(sd["truncated_encoder.0.weight"], donor.conv1.weight)
+    assert torch.equal(sd["truncated_encoder.6.5.bn3.running_var"], donor.layer3[5].bn3.running_var)
+    assert torch.equal(sd["classifier.weight"], before["classifier.weight"])        # head untouched
+
+    # (3) the three-section file of save_model_weights (what the README passes to --model_path) and DDP-prefixed dicts
+    three = tmp_path / "best_model_all.pth"
+    save_model_weights(model, str(three))
+    assert checkpoints.coverage(model, torch.load(three))["matched"] == 0
+    assert set(checkpoints.to_bare_encoder(torch.load(three))) == {k[len("truncated_encoder."):] for k in before
+                                                                   if k.startswith("truncated_encoder.")}
+    ddp_like = {"module." + k: v for k, v in model.state_dict().items()}
+    assert set(checkpoints.to_bare_encoder(ddp_like)) == set(checkpoints.to_bare_encoder(torch.load(three)))
+    assert checkpoints.to_bare_encoder(converted).keys() == converted.keys()        # idempotent

@@ -1,0 +1,30 @@
+"""The product under NCCL: a 2-rank DDP training step of the drop-in model equals the single-GPU step on the concatenated
+batch (eval-mode batch norm so that shard statistics do not enter). Needs two GPUs on the box:
+`gpurun --gpus 2 -- python -m pytest tests/test_gpu_distributed.py -m gpu`; skipped (not passed) with fewer."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def test_ddp_step_equals_single_gpu_step_on_the_concatenated_batch():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (one process per GPU over NCCL)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29731", os.path.join(ROOT, "tests", "tools", "ddp_worker.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    line = [ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1]
+    out = json.loads(line)
+    assert out["world"] == 2 and out["backend"] == "nccl"
+    # fp32 sums in another order (two shard means averaged by the all-reduce vs one mean over the batch)
+    assert out["worst_head_grad_rel"] <= 1e-4, out
+    assert out["worst_grad_rel"] <= 2e-3, out
+    assert out["worst_weight_rel"] <= 1e-4, out

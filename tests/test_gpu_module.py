@@ -1,7 +1,11 @@
 """The drop-in nn.Module on a B200 against the fp32 torch port of the reference on the same GPU and weights."""
+import os
+
 import numpy as np
 import pytest
 import torch
+
+from conftest import ROOT
 
 from oracle import head_fp64 as O
 from oracle.torch_port import PortModel
@@ -423,3 +427,86 @@ def test_inference_plan_on_odd_image_sizes_uses_the_direct_stem():
             m.fold_batchnorm = False
             e0, l0 = m(x)
         assert O.rel_err(npf(e1), npf(e0)) <= 2e-5 and O.rel_err(npf(l1), npf(l0)) <= 2e-5
+
+
+def test_mbarrier_timeout_traps_and_leaves_a_readable_record(tmp_path):
+    """A bounded mbarrier wait that expires records {code, block, thread, site} in mapped host memory and traps
+    (csrc/common.cuh): tests/tools/timeout_probe.cu waits on a barrier nobody arrives on with a 0.2 ms limit."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.isfile(nvcc):
+        pytest.skip("nvcc not available on this box")
+    exe = str(tmp_path / "timeout_probe")
+    src = os.path.join(ROOT, "tests", "tools", "timeout_probe.cu")
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", src, "-o", exe], check=True)
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "record=1 " in res.stdout and res.stdout.strip().endswith(" 777")
+
+
+@pytest.mark.parametrize("tf32,tol", [(True, 1e-3), (False, 1e-4)])
+def test_benched_configuration_matches_the_reference_port_directly(tf32, tol):
+    """The exact configuration bench.py times -- eval + no_grad, default channels_last execution with the folded-BN
+    inference plan, cuDNN TF32 convolutions as torch ships them, batch 64 at 224x224 -- against the fp32 port of the
+    reference (the reference's own op sequence, NCHW, same flags) on the same GPU and weights: embeddings / logits
+    <= 1e-3 normwise and identical argmax (BASELINE.json north_star); 1e-4 with TF32 convolutions off."""
+    from torchvision import models
+    from heuristique_style_transfer_code_b200 import TruncatedResNet50_for_test
+    saved = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = tf32
+    try:
+        torch.manual_seed(0)
+        ours = TruncatedResNet50_for_test(models.resnet50(weights=None), 7, 4, 32, device="cuda").eval()
+        port = PortModel(models.resnet50(weights=None), 7, 4, 32, device="cuda", return_embeddings=True).eval()
+        _randomise_batchnorm(ours)
+        port.load_state_dict(ours.state_dict())
+        assert ours.backbone_mode == "channels_last" and ours.fold_batchnorm
+        torch.manual_seed(1)
+        x = torch.randn(64, 3, 224, 224, device="cuda")
+        with torch.no_grad():
+            e1, l1 = ours(x)
+            assert ours._plan is not None                     # the folded plan ran
+            e2, l2 = port(x)
+        torch.cuda.synchronize()
+        assert O.rel_err(npf(e1), npf(e2)) <= tol and O.rel_err(npf(l1), npf(l2)) <= tol
+        assert torch.equal(l1.argmax(1), l2.argmax(1))
+    finally:
+        torch.backends.cudnn.allow_tf32 = saved
+
+
+@pytest.mark.parametrize("trunc", [5, 6, 8])
+def test_whole_module_at_other_truncation_depths(trunc):
+    """truncate_after_layer 5 / 6 / 8 (1 / 2 / 4 Gram stages; depth 8 adds layer4: 2048 channels at 7x7, k = 64, which the
+    default channels_last execution sends to the CTA-pair kernels): forward and backward against the port."""
+    from torchvision import models
+    from heuristique_style_transfer_code_b200 import TruncatedResNet50_for_test
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(0)
+    ours = TruncatedResNet50_for_test(models.resnet50(weights=None), trunc, 4, 32, device="cuda")
+    port = PortModel(models.resnet50(weights=None), trunc, 4, 32, device="cuda", return_embeddings=True)
+    port.load_state_dict(ours.state_dict())
+    assert ours.backbone_mode == "channels_last"
+    torch.manual_seed(1)
+    x = torch.randn(8, 3, 224, 224, device="cuda")
+    y = torch.randint(0, 4, (8,), device="cuda")
+    for mode in ("train", "eval"):
+        getattr(ours, mode)(); getattr(port, mode)()
+        ours.zero_grad(); port.zero_grad()
+        e1, l1 = ours(x)
+        e2, l2 = port(x)
+        torch.nn.functional.cross_entropy(l1, y).backward()
+        torch.nn.functional.cross_entropy(l2, y).backward()
+        torch.cuda.synchronize()
+        assert e1.shape == (8, 1024) and O.rel_err(npf(e1), npf(e2)) <= 1e-3 and O.rel_err(npf(l1), npf(l2)) <= 1e-3
+        assert torch.equal(l1.argmax(1), l2.argmax(1))
+        for (n, p1), (_, p2) in zip(ours.named_parameters(), port.named_parameters()):
+            if n.startswith(("attention", "classifier")):
+                assert O.rel_err(npf(p1.grad), npf(p2.grad)) <= 1e-2, (mode, n)
+            else:
+                assert p1.grad is not None and bool(torch.isfinite(p1.grad).all()), (mode, n)
+    with torch.no_grad():                                     # eval + no_grad: the folded inference plan at this depth
+        ours.eval(); port.eval()
+        e1, l1 = ours(x)
+        e2, l2 = port(x)
+    assert O.rel_err(npf(e1), npf(e2)) <= 1e-3 and torch.equal(l1.argmax(1), l2.argmax(1))

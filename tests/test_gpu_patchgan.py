@@ -141,8 +141,26 @@ def test_multiscale_matches_the_torch_port_and_refuses_grad_mode():
         pe, po = patchgan_multiscale_forward(m, x)
     assert rel(npf(emb), npf(pe)) < 1e-4 and rel(npf(out), npf(po)) < 1e-4
     assert len(m.get_gram_norms()) == sum(len(d.projection_layers) for d in m.scale_discriminators.values())
-    with pytest.raises(GramHeadError, match="inference-only"):
-        m(x)
+    # A forward that needs autograd history (upstream: style_transfer_patches, functions_Multi_PatchGAN.py:272-287, which
+    # backpropagates through the head to a noise image) is handed to the reference's OWN forward on this module's
+    # parameters; without a copy of the reference it is refused instead of returning tensors without history.
+    from heuristique_style_transfer_code_b200 import _reference
+    if _reference.reference_root(os.path.join("Models", "Models_Multi_PatchGAN.py")) is not None:
+        xg = x.clone().requires_grad_(True)
+        e2, o2 = m(xg)
+        assert e2.requires_grad and o2.requires_grad
+        assert rel(npf(e2), npf(emb)) < 1e-4 and rel(npf(o2), npf(out)) < 1e-4
+        e2.square().sum().backward()
+        assert xg.grad is not None and bool(torch.isfinite(xg.grad).all()) and float(xg.grad.abs().sum()) > 0
+    saved_root, saved_loaded = _reference.reference_root, dict(_reference._LOADED)
+    try:
+        _reference.reference_root = lambda rel_path: None
+        _reference._LOADED.clear()
+        with pytest.raises(GramHeadError, match="inference-only"):
+            m(x)
+    finally:
+        _reference.reference_root = saved_root
+        _reference._LOADED.update(saved_loaded)
 
 
 def test_nan_inputs_take_the_reference_replacement_path(capsys):

@@ -124,3 +124,21 @@ def test_port_is_bitwise_the_reference_live():
             assert torch.equal(ya[0], yb[0]) and torch.equal(ya[1], yb[1])
         else:
             assert torch.equal(ya, yb)
+
+
+def test_style_loss_oracle_matches_autograd_of_the_reference_ops():
+    """oracle.style_loss_and_grad against torch autograd of the reference's own op sequence
+    (gram_matrix: bmm + div(h*w), Models/...:26-30; mse_loss + backward, functions/...:291-295) in fp64."""
+    import torch
+    from oracle import head_fp64 as O
+    torch.manual_seed(0)
+    B, C, H, W = 2, 24, 5, 7
+    x = torch.randn(B, C, H, W, dtype=torch.float64).relu()
+    target = torch.randn(B, C, C, dtype=torch.float64)
+    xr = x.clone().requires_grad_(True)
+    feats = xr.view(B, C, H * W)
+    loss = torch.nn.functional.mse_loss(torch.bmm(feats, feats.transpose(1, 2)).div(H * W), target)
+    loss.backward()
+    got_loss, got_df = O.style_loss_and_grad(x.numpy().reshape(B, C, H * W), target.numpy())
+    assert abs(got_loss - loss.item()) <= 1e-14 * abs(loss.item())
+    assert O.rel_err(got_df.reshape(B, C, H, W), xr.grad.numpy()) <= 1e-14
