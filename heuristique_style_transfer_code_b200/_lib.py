@@ -28,9 +28,9 @@ _SIGNATURES = {
     "gh_adaptive_pool_fwd": (c_int, [_P, c_int, c_int, c_int, _P, c_int, c_int, _P]),
     "gh_adaptive_pool_bwd": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "gh_gram_pool_bwd": (c_int, [_P, c_int, c_longlong, c_longlong, c_longlong, c_int, c_int, c_int, c_int, _P, c_int,
-                                  c_int, _P, c_longlong, c_longlong, c_longlong, c_int, _P]),
-    "gh_gram_dense_bwd": (c_int, [_P, c_int, c_longlong, c_longlong, c_longlong, c_int, c_int, c_int, _P, _P, c_longlong,
-                                   c_longlong, c_longlong, c_int, _P]),
+                                  c_int, _P, c_int, c_longlong, c_longlong, c_longlong, c_int, _P]),
+    "gh_gram_dense_bwd": (c_int, [_P, c_int, c_longlong, c_longlong, c_longlong, c_int, c_int, c_int, _P, _P, c_int,
+                                   c_longlong, c_longlong, c_longlong, c_int, _P]),
     "gh_attn_head_fwd": (c_int, [_P] * 7 + [c_int] * 4 + [_P] * 5 + [_P]),
     "gh_transpose_cast": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_longlong, _P]),
     "gh_preprocess_frame": (c_int, [_P, c_longlong, c_int, c_int, c_int, _P, _P, _P, c_int, _P, _P, _P, c_int, _P, _P, _P,

@@ -30,17 +30,18 @@ namespace gh {
 // Two rings. The generated A tiles have a short refill round trip (commit -> empty -> 8 stores -> proxy fence -> remote
 // arrive, well under a microsecond), the F tiles come from HBM / L2 with 1-2 us of loaded latency: bytes in flight =
 // bandwidth x latency, so the B ring is as deep as shared memory allows and the A ring only as deep as it must be.
-#ifndef GH_BP_A_STAGES
-#define GH_BP_A_STAGES 5
-#endif
-#ifndef GH_BP_B_STAGES
-#define GH_BP_B_STAGES 5
-#endif
 #ifndef GH_BP_STORE_BUFS
 #define GH_BP_STORE_BUFS 3
 #endif
-constexpr int kBpAStages = GH_BP_A_STAGES;                  // A ring; generator group i fills A stages i, i + 4, ...
-constexpr int kBpBStages = GH_BP_B_STAGES;                  // B ring (TMA loads of F)
+// Ring depths are launch parameters (GramBwdPairParams::a_stages / b_stages, a_stages + b_stages <= kBpRingTiles): the
+// HBM-bound C = 256 stage is fastest with 5 + 5 (a deeper F ring is 20 % slower there), the C >= 512 stages -- whose F
+// tiles come mostly from L2 and whose generated A chunks shrink with the pooling factor -- want the F ring as deep as
+// shared memory allows (bytes in flight = bandwidth x latency).
+// a_stages >= kBpGroups: generator group i produces the chunks n = i (mod 4); its next chunk n + 4 reuses the stage of
+// chunk n + 4 - a_stages, which must be a chunk this group (or an earlier one) has already PUBLISHED -- otherwise its
+// wait on the stage's `empty` barrier could run two phases ahead of the barrier and pass on the aliased parity.
+constexpr int kBpRingTiles = 10;                            // A stages + B stages
+constexpr int kBpMaxStages = 12;                            // per ring (sizes the barrier arrays)
 constexpr uint32_t kBpTileBytes = 16384;                    // A: [128 c][128 B]; B: <= 128 x-columns x (K chunk) x elem
 constexpr int kBpStoreBufs = GH_BP_STORE_BUFS;              // staging tiles per epilogue warp = TMA stores it keeps in flight
 constexpr uint32_t kBpStoreBytes = 4 * kBpStoreBufs * 4096; // per epilogue warp: kBpStoreBufs [32 c][32 x] fp32 staging tiles
@@ -48,7 +49,7 @@ constexpr int kBpMaxG = 32;                                 // pooled size handl
 constexpr int kBpGroups = 4;                                // generator groups (four warps each); group i generates chunks n = i mod 4
 constexpr int kBpTableFloats = kBpMaxG * kBpMaxG + kBpMaxG; // g x g table + one row of zeros (rows beyond C)
 constexpr uint32_t kBpSymBytes = 2 * kBpTableFloats * 4;    // current and next image's table, shared by the groups
-constexpr uint32_t kBpSmemBytes = (kBpAStages + kBpBStages) * kBpTileBytes + kBpStoreBytes + kBpSymBytes + 1024 + 256;
+constexpr uint32_t kBpSmemBytes = kBpRingTiles * kBpTileBytes + kBpStoreBytes + kBpSymBytes + 1024 + 512;
 constexpr int kBpGroupThreads = 128;                        // one thread per A row
 constexpr int kBpGenThreads = kBpGroups * kBpGroupThreads;
 constexpr int kBpProducer2Warp = 6 + kBpGenThreads / 32;    // second TMA producer warp (the last one)
@@ -67,6 +68,12 @@ struct GramBwdPairParams {
   int nHT, nCB;             // x tiles, 256-channel output blocks
   int nkc;                  // K chunks (32 input channels for tf32, 64 for bf16)
   int total_units;
+  int areuse;               // POOL: consecutive k-steps of a chunk whose A data is identical (1, 2 or 4), see below
+  int a_stages, b_stages;   // ring depths (A: generated gradient tiles, B: TMA-loaded F tiles)
+  int b_stage_bytes;        // bytes of one F stage (a multiple of 1024): the F ring takes the (kBpRingTiles - a_stages)
+                            // tiles the A ring leaves, cut into stages of the size the x-tile width needs
+  int df_bf16;              // 1: dF leaves as bf16 (tmD is a bf16 map, 64 B swizzle): half the gradient bytes, and the
+                            //    gradient a bf16 backbone wants; 0: fp32
 };
 
 struct GramBwdPairUnit {
@@ -103,15 +110,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_ring = smem_base;                                        // kBpAStages x 16 KB
-  const uint32_t b_ring = a_ring + kBpAStages * kBpTileBytes;               // kBpBStages x 16 KB
-  const uint32_t store_smem = b_ring + kBpBStages * kBpTileBytes;
+  const uint32_t kBpAStages = (uint32_t)p.a_stages, kBpBStages = (uint32_t)p.b_stages;   // launch parameters
+  const uint32_t a_ring = smem_base;                                        // a_stages x 16 KB
+  const uint32_t b_ring = a_ring + kBpAStages * kBpTileBytes;               // b_stages x 16 KB
+  const uint32_t store_smem = smem_base + kBpRingTiles * kBpTileBytes;
   const uint32_t sym_smem = store_smem + kBpStoreBytes;
   float* sym = reinterpret_cast<float*>(smem_raw + (sym_smem - smem_u32(smem_raw)));
   const uint32_t bars = sym_smem + kBpSymBytes;
-  const uint32_t bar_fullA = bars, bar_emptyA = bar_fullA + 8 * kBpAStages;
-  const uint32_t bar_fullB = bar_emptyA + 8 * kBpAStages, bar_emptyB = bar_fullB + 8 * kBpBStages;
-  const uint32_t bar_tfull = bar_emptyB + 8 * kBpBStages, bar_tempty = bar_tfull + 16;
+  const uint32_t bar_fullA = bars, bar_emptyA = bar_fullA + 8 * kBpMaxStages;
+  const uint32_t bar_fullB = bar_emptyA + 8 * kBpMaxStages, bar_emptyB = bar_fullB + 8 * kBpMaxStages;
+  const uint32_t bar_tfull = bar_emptyB + 8 * kBpMaxStages, bar_tempty = bar_tfull + 16;
   const uint32_t tmem_slot = bar_tempty + 16;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -127,11 +135,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmF);
     tma_prefetch_desc(&tmD);
-    for (int s = 0; s < kBpAStages; ++s) {
+    for (uint32_t s = 0; s < kBpAStages; ++s) {
       mbar_init(bar_fullA + 8 * s, 2 * (kBpGroupThreads / 32));   // the stage's generator warps of both CTAs
       mbar_init(bar_emptyA + 8 * s, 1);                           // multicast tcgen05.commit
     }
-    for (int s = 0; s < kBpBStages; ++s) {
+    for (uint32_t s = 0; s < kBpBStages; ++s) {
       mbar_init(bar_fullB + 8 * s, 1);                            // leader's expect_tx; both CTAs' TMA bytes land on it
       mbar_init(bar_emptyB + 8 * s, 1);
     }
@@ -171,7 +179,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
           const uint32_t stage = n % (uint32_t)kBpBStages, phase = (n / (uint32_t)kBpBStages) & 1u;
           mbar_wait(bar_emptyB + 8 * stage, phase ^ 1u, 100u + stage);
           if (rank == 0) mbar_arrive_expect_tx(bar_fullB + 8 * stage, tx_bytes);
-          const uint32_t b_tile = b_ring + stage * kBpTileBytes;
+          const uint32_t b_tile = b_ring + stage * (uint32_t)p.b_stage_bytes;
           if constexpr (NHWC) {
             tma_load_3d_pair(b_tile, &tmF, fullB_leader + 8 * stage, kc * (int)KC, x0, w.b);
           } else {
@@ -196,7 +204,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
                                 : (KIND == KIND_TF32 ? make_smem_desc_sw128b32_mnmajor(b_ring, kAtomBytesB)
                                                      : make_smem_desc_sw128_mnmajor(b_ring, kAtomBytesB));
       constexpr uint64_t kStageInc = kBpTileBytes >> 4, kAInc = 32u >> 4, kBInc = NHWC ? 32u >> 4 : kStepBytesB >> 4;
+      const uint64_t kStageIncB = (uint64_t)p.b_stage_bytes >> 4;
       const int full_chunks = p.C / (int)KC;
+      const uint32_t amask = (MODE == GRAM_POOL) ? (~((uint32_t)p.areuse - 1u) & 3u) : 3u;
+      const uint64_t a1 = (1u & amask) * kAInc, a2 = (2u & amask) * kAInc, a3 = (3u & amask) * kAInc;
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
       for (int u = u_begin; u < u_end; ++u, ++it) {
         const uint32_t ab = it & 1u, use = it >> 1;
@@ -207,16 +218,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
           mbar_wait_cl(bar_fullA + 8 * sa, pa, 300u + sa);
           mbar_wait_cl(bar_fullB + 8 * sb, pb, 320u + sb);
           tc_fence_after_sync();
-          const uint64_t da = dA0 + sa * kStageInc, db = dB0 + sb * kStageInc;
+          const uint64_t da = dA0 + sa * kStageInc, db = dB0 + sb * kStageIncB;
+          // k-step ks reads the A data of k-step (ks & amask): with a pooling factor k >= 2 * UMMA_K the generated rows
+          // repeat across k-steps, so only the first k-step of each run is generated (a1..a3 = 0/0/0, 1/2/2 or 1/2/3)
           if (kc < full_chunks) {
             umma2<KIND>(acc, da, db, idesc, kc != 0 ? 1u : 0u);
-            umma2<KIND>(acc, da + kAInc, db + kBInc, idesc, 1u);
-            umma2<KIND>(acc, da + 2 * kAInc, db + 2 * kBInc, idesc, 1u);
-            umma2<KIND>(acc, da + 3 * kAInc, db + 3 * kBInc, idesc, 1u);
+            umma2<KIND>(acc, da + a1, db + kBInc, idesc, 1u);
+            umma2<KIND>(acc, da + a2, db + 2 * kBInc, idesc, 1u);
+            umma2<KIND>(acc, da + a3, db + 3 * kBInc, idesc, 1u);
           } else {
             for (uint32_t ks = 0; ks < KC / T::kUmmaK; ++ks) {
               if ((int)(kc * KC + ks * T::kUmmaK) >= p.C) break;
-              umma2<KIND>(acc, da + ks * kAInc, db + ks * kBInc, idesc, (uint32_t)kc | ks);
+              umma2<KIND>(acc, da + (ks & amask) * kAInc, db + ks * kBInc, idesc, (uint32_t)kc | ks);
             }
           }
           umma_commit2(bar_emptyA + 8 * sa);
@@ -248,7 +261,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
         tmem_ld32(taddr + (uint32_t)n0, v);
         if (elected) tma_store_wait_read<kBpStoreBufs - 1>();     // the staging tile about to be reused has been read
         __syncwarp();
-        if constexpr (NHWC) {
+        if (p.df_bf16) {
+          // bf16 gradient: 64 B rows, SWIZZLE_64B (16 B chunk c of row r sits at chunk c ^ ((r >> 1) & 3))
+          if constexpr (NHWC) {
+            // [32 x rows][32 channels]: lane (= channel) writes element `lane` of every row
+            const uint32_t tile = my_store + buf * 4096u + (((uint32_t)lane & 7u) << 1);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const uint32_t addr = tile + (uint32_t)j * 64u + (((((uint32_t)lane >> 3) ^ (((uint32_t)j >> 1) & 3u))) << 4);
+              const __nv_bfloat16 h = __float2bfloat16_rn(v[j] * p.scale);
+              asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(*reinterpret_cast<const unsigned short*>(&h)) : "memory");
+            }
+          } else {
+            // [32 channel rows][32 x]: lane (= channel) writes its row as four 16 B chunks
+            const uint32_t tile = my_store + buf * 4096u + (uint32_t)lane * 64u, sw64 = ((uint32_t)lane >> 1) & 3u;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              sts_u4(tile + ((((uint32_t)c) ^ sw64) << 4), pack_bf16x2(v[8 * c] * p.scale, v[8 * c + 1] * p.scale),
+                     pack_bf16x2(v[8 * c + 2] * p.scale, v[8 * c + 3] * p.scale),
+                     pack_bf16x2(v[8 * c + 4] * p.scale, v[8 * c + 5] * p.scale),
+                     pack_bf16x2(v[8 * c + 6] * p.scale, v[8 * c + 7] * p.scale));
+          }
+        } else if constexpr (NHWC) {
           // staging tile = [32 x rows][32 channels]: lane (= channel) writes column `lane` of every row; one row is 32
           // consecutive words across the warp (16 B chunks XOR-swizzled by the row), so the stores are conflict-free
           const uint32_t tile = my_store + buf * 4096u + (((uint32_t)lane & 3u) << 2);
@@ -346,17 +380,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
         const uint32_t a_row = a_ring + stage * kBpTileBytes + row_off;
         const int dbase = kc * (int)KC;
         if (MODE == GRAM_POOL) {
+          // A k-step is two 16 B chunks of the row. Only the k-steps the MMAs read are written: all four when the
+          // pooling factor equals UMMA_K, every second one / the first one when it is 2x / >= 4x UMMA_K (p.areuse).
           const bool full_chunk = dbase + (int)KC <= p.C;
-          float v[8];
+          const int jstep = 2 * p.areuse;
+          for (int j0 = 0; j0 < 8; j0 += jstep) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int d0 = dbase + j * EPC;
-            v[j] = (full_chunk || d0 < p.C) ? srow[d0 >> p.kshift] : 0.f;
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t t = (KIND == KIND_TF32) ? f32_to_tf32_rna(v[j]) : pack_bf16x2(v[j], v[j]);
-            sts_u4(a_row + ((((uint32_t)j) ^ sw) << 4), t, t, t, t);
+            for (int jj = 0; jj < 2; ++jj) {
+              const int j = j0 + jj;
+              const int d0 = dbase + j * EPC;
+              const float v = (full_chunk || d0 < p.C) ? srow[d0 >> p.kshift] : 0.f;
+              const uint32_t t = (KIND == KIND_TF32) ? f32_to_tf32_rna(v) : pack_bf16x2(v, v);
+              sts_u4(a_row + ((((uint32_t)j) ^ sw) << 4), t, t, t, t);
+            }
           }
         } else {
           const float* gb = p.dG + (long long)w.b * p.C * p.C;

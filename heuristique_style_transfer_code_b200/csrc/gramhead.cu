@@ -116,7 +116,8 @@ static cudaError_t launch_gram_fwd_kp(const GramFwdParams& p, int kp, int grid, 
 // Pair (cta_group::2, TMA-staged) kernels. -1 = auto, 0 = never, 1 = whenever TMA can describe the tensors.
 static int g_opt_fwd_pair = -1;
 static int g_opt_bwd_pair = -1;
-static int g_opt_bwd_nt = 0;        // 0 = plan the x-tile width; 64..256 (multiple of 32) forces it (experiments)
+static int g_opt_bwd_nt = 0;        // 0 = plan the x-tile width; 64..256 (multiple of 16) forces it (experiments)
+static int g_opt_bwd_stages = 0;    // 0 = by shape; a * 16 + b forces the A / B ring depths of the pair backward
 static int g_opt_tma_f32_type = 1;  // tensor-map data type for fp32 features: 0 = FLOAT32, 1 = TFLOAT32
 
 template <int KIND, int KP, bool NHWC>
@@ -244,10 +245,13 @@ static int gram_fwd_common(const void* F, int f_dtype, long long img_stride, lon
 
 static int gram_bwd_common(const void* F, int f_dtype, long long img_stride, long long row_stride, long long x_stride,
                            int B, int C, int HW, int mode, int g, const float* dP, long long dp_img_stride,
-                           const float* dG, float* dF, long long df_img_stride, long long df_row_stride,
+                           const float* dG, void* dF_any, int df_dtype, long long df_img_stride, long long df_row_stride,
                            long long df_x_stride, int max_ctas, cudaStream_t st) {
+  float* dF = reinterpret_cast<float*>(dF_any);
   if (!F || !dF || B <= 0 || C <= 0 || HW <= 0) return GH_ERR_BAD_ARG;
   if (f_dtype != GH_DTYPE_F32 && f_dtype != GH_DTYPE_BF16) return GH_ERR_BAD_ARG;
+  if (df_dtype != GH_DTYPE_F32 && df_dtype != GH_DTYPE_BF16) return GH_ERR_BAD_ARG;
+  const bool df16 = (df_dtype == GH_DTYPE_BF16);   // bf16 gradient: CTA-pair kernels only (GH_ERR_UNSUPPORTED otherwise)
   const bool nhwc = (x_stride != 1);     // F and dF share the layout: both NCHW-like or both channels_last
   if (x_stride <= 0 || row_stride <= 0 || df_x_stride <= 0 || df_row_stride <= 0) return GH_ERR_BAD_ARG;
   if (nhwc != (df_x_stride != 1) || (nhwc && (row_stride != 1 || df_row_stride != 1))) return GH_ERR_BAD_ARG;
@@ -284,18 +288,37 @@ static int gram_bwd_common(const void* F, int f_dtype, long long img_stride, lon
       if (nhwc)     // F: K-major tiles [NT/2 position rows][128 B of channels]; dF: [32 x][32 c] tiles
         mapped = make_tensor_map_nhwc_cxb(&tmF, F, is_bf16, img_stride, x_stride, B, C, HW, kc_elems, q.NT / 2,
                                           g_opt_tma_f32_type) &&
-                 make_tensor_map_nhwc_cxb(&tmD, dF, false, df_img_stride, df_x_stride, B, C, HW, 32, 32, 0);
+                 make_tensor_map_nhwc_cxb(&tmD, dF, df16, df_img_stride, df_x_stride, B, C, HW, 32, 32, 0, /*swizzle64=*/df16);
       else
         mapped = make_tensor_map_xcb(&tmF, F, is_bf16, img_stride, row_stride, B, C, HW, kc_elems, kc_elems,
                                      g_opt_tma_f32_type, /*atom32=*/!is_bf16) &&
-                 make_tensor_map_xcb(&tmD, dF, false, df_img_stride, df_row_stride, B, C, HW, 32, 32, 0);
+                 make_tensor_map_xcb(&tmD, dF, df16, df_img_stride, df_row_stride, B, C, HW, 32, 32, 0, false, /*swizzle64=*/df16);
     }
     if (mapped) {
       q.B = B; q.C = C; q.HW = HW; q.mode = mode;
       q.dP = dP; q.dp_img_stride = dp_img_stride; q.g = g; q.kshift = p.kshift; q.dG = dG;
       q.scale = p.scale;
+      q.df_bf16 = df16 ? 1 : 0;
+      // ring depths: see gram_bwd_pair.cuh. C = 256 is HBM-bound and fastest at 5 + 5; wider stages re-read F from L2
+      // and are bound by the bytes the F ring keeps in flight.
+      q.a_stages = 5; q.b_stages = 5;
+      if (C >= 512) { q.a_stages = 4; q.b_stages = kBpMaxStages; }
+      if (g_opt_bwd_stages) { q.a_stages = g_opt_bwd_stages >> 4; q.b_stages = g_opt_bwd_stages & 15; }
+      {   // one F stage: NHWC [NT/2 position rows][128 B]; NCHW: ceil(NT/2 / KC) x-blocks of [KC k-rows][128 B]
+        const int half = q.NT / 2;
+        long long sb = nhwc ? (long long)half * 128 : (long long)((half + kc_elems - 1) / kc_elems) * kc_elems * 128;
+        sb = (sb + 1023) / 1024 * 1024;
+        q.b_stage_bytes = (int)sb;
+        const long long fit = ((long long)(kBpRingTiles - q.a_stages) * kBpTileBytes) / sb;
+        if (q.b_stages > fit) q.b_stages = (int)fit;
+        if (q.b_stages > kBpMaxStages) q.b_stages = kBpMaxStages;
+      }
       q.nCB = (C + 255) / 256;
       q.nkc = (C + kc_elems - 1) / kc_elems;
+      {   // k-steps of a chunk that share one generated piece of A: pooling factor / UMMA_K, capped at the 4 of a chunk
+        const int umma_k = is_bf16 ? 16 : 8, kfac = (mode == GRAM_POOL) ? (C / g) : 1;
+        q.areuse = kfac >= 4 * umma_k ? 4 : (kfac >= 2 * umma_k ? 2 : 1);
+      }
       const long long tot = (long long)B * q.nHT * q.nCB;
       if (tot <= 0x7fffffffLL) {
         q.total_units = (int)tot;
@@ -324,7 +347,7 @@ static int gram_bwd_common(const void* F, int f_dtype, long long img_stride, lon
       }
     }
   }
-  if (nhwc) return GH_ERR_UNSUPPORTED;   // the ld.global kernels read / write NCHW rows only: the caller transposes
+  if (nhwc || df16) return GH_ERR_UNSUPPORTED;   // the ld.global kernels read / write fp32 NCHW rows only
   if (g_opt_bwd_variant == 2) {
     GramBwd2Params q;
     q.F = F; q.img_stride = img_stride; q.row_stride = row_stride;
@@ -476,8 +499,14 @@ int gh_set_option(const char* name, int value) {
     return 0;
   }
   if (key == "gram_bwd_nt") {
-    if (value != 0 && (value < 64 || value > 256 || value % 32)) return GH_ERR_BAD_ARG;
+    if (value != 0 && (value < 64 || value > 256 || value % 16)) return GH_ERR_BAD_ARG;
     g_opt_bwd_nt = value;
+    return 0;
+  }
+  if (key == "gram_bwd_stages") {
+    const int a = value >> 4, b = value & 15;
+    if (value != 0 && (a < kBpGroups || b < 2 || a > kBpRingTiles - 2 || b > kBpMaxStages)) return GH_ERR_BAD_ARG;
+    g_opt_bwd_stages = value;
     return 0;
   }
   if (key == "tma_f32_type") {
@@ -558,19 +587,19 @@ int gh_adaptive_pool_bwd(const float* d_desc, int l, int L, int B, int C, int g,
 }
 
 int gh_gram_pool_bwd(const void* F, int f_dtype, long long img_stride, long long row_stride, long long x_stride, int B,
-                     int C, int HW, int g, const float* d_desc, int l, int L, float* dF, long long df_img_stride,
-                     long long df_row_stride, long long df_x_stride, int max_ctas, void* stream) {
+                     int C, int HW, int g, const float* d_desc, int l, int L, void* dF, int df_dtype,
+                     long long df_img_stride, long long df_row_stride, long long df_x_stride, int max_ctas, void* stream) {
   if (!d_desc || l < 0 || l >= L || g <= 0) return GH_ERR_BAD_ARG;
   return gram_bwd_common(F, f_dtype, img_stride, row_stride, x_stride, B, C, HW, GRAM_POOL, g,
-                         d_desc + (long long)l * g * g, (long long)L * g * g, nullptr, dF, df_img_stride, df_row_stride,
-                         df_x_stride, max_ctas, (cudaStream_t)stream);
+                         d_desc + (long long)l * g * g, (long long)L * g * g, nullptr, dF, df_dtype, df_img_stride,
+                         df_row_stride, df_x_stride, max_ctas, (cudaStream_t)stream);
 }
 
 int gh_gram_dense_bwd(const void* F, int f_dtype, long long img_stride, long long row_stride, long long x_stride, int B,
-                      int C, int HW, const float* dG, float* dF, long long df_img_stride, long long df_row_stride,
-                      long long df_x_stride, int max_ctas, void* stream) {
+                      int C, int HW, const float* dG, void* dF, int df_dtype, long long df_img_stride,
+                      long long df_row_stride, long long df_x_stride, int max_ctas, void* stream) {
   return gram_bwd_common(F, f_dtype, img_stride, row_stride, x_stride, B, C, HW, GRAM_DENSE, 0, nullptr, 0, dG, dF,
-                         df_img_stride, df_row_stride, df_x_stride, max_ctas, (cudaStream_t)stream);
+                         df_dtype, df_img_stride, df_row_stride, df_x_stride, max_ctas, (cudaStream_t)stream);
 }
 
 int gh_attn_head_fwd(const float* desc, const float* W_in, const float* b_in, const float* W_out, const float* b_out,

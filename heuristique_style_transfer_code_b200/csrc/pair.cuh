@@ -213,12 +213,12 @@ inline PFN_encodeTiled get_encode_tiled() {
 // atom32: 128 B swizzle with a 32 B atom (MN-major tf32 operands) instead of the plain 128 B swizzle.
 inline bool make_tensor_map_xcb(CUtensorMap* map, const void* base, bool is_bf16, long long img_stride,
                                 long long row_stride, int B, int C, int HW, int box_x, int box_c, int f32_type = 0,
-                                bool atom32 = false) {
+                                bool atom32 = false, bool swizzle64 = false) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return false;
   const long long es = is_bf16 ? 2 : 4;
   if ((reinterpret_cast<uintptr_t>(base) & 15u) || (row_stride * es) % 16 || (img_stride * es) % 16) return false;
-  if (row_stride < HW || img_stride <= 0 || box_x * es != 128 || box_c > 256 || box_c < 1) return false;
+  if (row_stride < HW || img_stride <= 0 || box_x * es != (swizzle64 ? 64 : 128) || box_c > 256 || box_c < 1) return false;
   if (row_stride * es >= (1LL << 40) || img_stride * es >= (1LL << 40)) return false;
   cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)C, (cuuint64_t)B};
   cuuint64_t strides[2] = {(cuuint64_t)(row_stride * es), (cuuint64_t)(img_stride * es)};
@@ -228,7 +228,8 @@ inline bool make_tensor_map_xcb(CUtensorMap* map, const void* base, bool is_bf16
                                  : (f32_type == 1 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
   CUresult r = enc(map, dt, 3,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                             : (atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -261,12 +262,13 @@ inline bool make_tensor_map_nhwc_mn(CUtensorMap* map, const void* base, bool is_
 // The same tensor as a 3-D map (c, x, b) with a box of box_c x box_x x 1 and the plain 128 B swizzle: K-major operand
 // tiles whose K index is the channel (the backward's F operand: [x rows][128 B of channels]) and the NHWC gradient store.
 inline bool make_tensor_map_nhwc_cxb(CUtensorMap* map, const void* base, bool is_bf16, long long img_stride,
-                                     long long x_stride, int B, int C, int HW, int box_c, int box_x, int f32_type) {
+                                     long long x_stride, int B, int C, int HW, int box_c, int box_x, int f32_type,
+                                     bool swizzle64 = false) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return false;
   const long long es = is_bf16 ? 2 : 4;
   if ((reinterpret_cast<uintptr_t>(base) & 15u) || (x_stride * es) % 16 || (img_stride * es) % 16) return false;
-  if (x_stride < C || img_stride <= 0 || box_c * es != 128 || box_x < 1 || box_x > 256) return false;
+  if (x_stride < C || img_stride <= 0 || box_c * es != (swizzle64 ? 64 : 128) || box_x < 1 || box_x > 256) return false;
   if (x_stride * es >= (1LL << 40) || img_stride * es >= (1LL << 40)) return false;
   cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)HW, (cuuint64_t)B};
   cuuint64_t strides[2] = {(cuuint64_t)(x_stride * es), (cuuint64_t)(img_stride * es)};
@@ -275,7 +277,8 @@ inline bool make_tensor_map_nhwc_cxb(CUtensorMap* map, const void* base, bool is
   const CUtensorMapDataType dt = is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                                  : (f32_type == 1 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
   CUresult r = enc(map, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 

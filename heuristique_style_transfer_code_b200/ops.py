@@ -108,15 +108,15 @@ def nhwc_to_nchw(x: torch.Tensor) -> torch.Tensor:
 
 
 def grad_like_activation(df: torch.Tensor, shape, dtype, channels_last: bool) -> torch.Tensor:
-    """fp32 (B, C, HW) gradient -> gradient tensor of the activation's shape and dtype; for a channels_last activation
+    """(B, C, HW) gradient (fp32 or bf16) -> gradient tensor of the activation's shape and dtype; for a channels_last activation
     the transpose kernel writes it NHWC (and casts) directly, so the cuDNN backward gets the layout it runs in."""
     if not channels_last:
         return df.view(shape).to(dtype)
     b, c, h, w = shape
     out = torch.empty((b, c, h, w), dtype=dtype, device=df.device, memory_format=torch.channels_last)
-    work = dict(bytes=df.numel() * (4 + out.element_size()), flops=0, kind="transpose")
+    work = dict(bytes=df.numel() * (df.element_size() + out.element_size()), flops=0, kind="transpose")
     with torch.cuda.device(df.device), _Timed(f"nchw_to_nhwc[C={c},HW={h * w},{dtype}]", 1, df.device, **work):
-        rc = _lib.lib().gh_transpose_cast(df.data_ptr(), GH_DTYPE_F32, out.data_ptr(), _dtype_code(out), b, c, h * w, c,
+        rc = _lib.lib().gh_transpose_cast(df.data_ptr(), _dtype_code(df), out.data_ptr(), _dtype_code(out), b, c, h * w, c,
                                           _stream_ptr(df))
     check(rc, "gh_transpose_cast")
     return out
@@ -175,35 +175,55 @@ def gram_dense_fwd(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def _grad_buffer(x: torch.Tensor, s_x: int, b: int, c: int, hw: int):
-    """fp32 dF in the layout of the features: (B, C, HW) rows, or channels_last like x. -> (tensor, img, row, x strides)"""
+def _grad_buffer(x: torch.Tensor, s_x: int, b: int, c: int, hw: int, dtype=torch.float32):
+    """dF in the layout of the features: (B, C, HW) rows, or channels_last like x. -> (tensor, img, row, x strides)"""
     if s_x == 1:
-        return torch.empty((b, c, hw), device=x.device, dtype=torch.float32), c * hw, hw, 1
-    df = torch.empty(x.shape, device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
+        return torch.empty((b, c, hw), device=x.device, dtype=dtype), c * hw, hw, 1
+    df = torch.empty(x.shape, device=x.device, dtype=dtype, memory_format=torch.channels_last)
     return df, c * hw, 1, c
 
 
-def gram_pool_bwd(x: torch.Tensor, g: int, d_desc: torch.Tensor, l: int) -> torch.Tensor:
-    """-> fp32 dF, (B, C, HW) for x-contiguous features, channels_last (B, C, H, W) for channels_last features."""
+# bf16 activations (the opt-in bf16 backbone modes) get their gradient written as bf16 by the backward kernel itself --
+# half the HBM bytes of the fp32 gradient and no separate cast pass -- whenever the CTA-pair kernels take the shape.
+BF16_GRADIENTS = True
+
+
+def _gram_bwd_call(entry, name, x, args_mid, work_extra):
+    """Shared launch logic of the pooled / dense backward: try the bf16 gradient for bf16 features, fall back to fp32."""
     x, code, s_img, s_row, s_x, b, c, hw = _feature_view(x)
+    want16 = BF16_GRADIENTS and x.dtype == torch.bfloat16
+    for dtype in ((torch.bfloat16, torch.float32) if want16 else (torch.float32,)):
+        df, d_img, d_row, d_x = _grad_buffer(x, s_x, b, c, hw, dtype)
+        work = dict(bytes=b * c * hw * (x.element_size() + df.element_size()) + work_extra, flops=2 * b * c * c * hw,
+                    kind="gram_bwd")
+        tag = ",bf16out" if dtype == torch.bfloat16 else ""
+        with torch.cuda.device(x.device), _Timed(f"{name}[C={c},HW={hw},{x.dtype}{_layout_tag(s_x)}{tag}]", 1, x.device, **work):
+            rc = entry(x.data_ptr(), code, s_img, s_row, s_x, b, c, hw, *args_mid, df.data_ptr(), _dtype_code(df), d_img, d_row,
+                       d_x, MAX_CTAS, _stream_ptr(x))
+        if rc == _lib.GH_ERR_UNSUPPORTED and dtype == torch.bfloat16:
+            global LAUNCHES                                   # nothing was launched: take the attempt out of the accounting
+            LAUNCHES -= 1
+            if PROFILE and PROFILE[-1][0].endswith("bf16out]"):
+                PROFILE.pop()
+            continue
+        return rc, df
+    return rc, df
+
+
+def gram_pool_bwd(x: torch.Tensor, g: int, d_desc: torch.Tensor, l: int) -> torch.Tensor:
+    """-> dF, (B, C, HW) for x-contiguous features, channels_last (B, C, H, W) for channels_last features; fp32, or bf16
+    for bf16 features on the CTA-pair kernels (BF16_GRADIENTS)."""
     d_desc = d_desc.contiguous()
-    df, d_img, d_row, d_x = _grad_buffer(x, s_x, b, c, hw)
-    work = dict(bytes=b * c * hw * (x.element_size() + 4) + b * g * g * 4, flops=2 * b * c * c * hw, kind="gram_bwd")
-    with torch.cuda.device(x.device), _Timed(f"gram_pool_bwd[C={c},HW={hw},{x.dtype}{_layout_tag(s_x)}]", 1, x.device, **work):
-        rc = _lib.lib().gh_gram_pool_bwd(x.data_ptr(), code, s_img, s_row, s_x, b, c, hw, g, d_desc.data_ptr(), l,
-                                         d_desc.shape[1], df.data_ptr(), d_img, d_row, d_x, MAX_CTAS, _stream_ptr(x))
+    b = d_desc.shape[0]
+    rc, df = _gram_bwd_call(_lib.lib().gh_gram_pool_bwd, "gram_pool_bwd", x, (g, d_desc.data_ptr(), l, d_desc.shape[1]),
+                            b * g * g * 4)
     check(rc, "gh_gram_pool_bwd")
     return df
 
 
 def gram_dense_bwd(x: torch.Tensor, d_gram: torch.Tensor) -> torch.Tensor:
-    x, code, s_img, s_row, s_x, b, c, hw = _feature_view(x)
     d_gram = d_gram.contiguous().float()
-    df, d_img, d_row, d_x = _grad_buffer(x, s_x, b, c, hw)
-    work = dict(bytes=b * c * hw * (x.element_size() + 4) + b * c * c * 4, flops=2 * b * c * c * hw, kind="gram_bwd")
-    with torch.cuda.device(x.device), _Timed(f"gram_dense_bwd[C={c},HW={hw},{x.dtype}{_layout_tag(s_x)}]", 1, x.device, **work):
-        rc = _lib.lib().gh_gram_dense_bwd(x.data_ptr(), code, s_img, s_row, s_x, b, c, hw, d_gram.data_ptr(),
-                                          df.data_ptr(), d_img, d_row, d_x, MAX_CTAS, _stream_ptr(x))
+    rc, df = _gram_bwd_call(_lib.lib().gh_gram_dense_bwd, "gram_dense_bwd", x, (d_gram.data_ptr(),), d_gram.numel() * 4)
     check(rc, "gh_gram_dense_bwd")
     return df
 

@@ -76,17 +76,19 @@ int gh_adaptive_pool_bwd(const float* d_desc, int l, int L, int B, int C, int g,
 
 /* Pooled Gram, backward (autograd of the three reference lines above):
  *   dF[b] = (dG + dG^T) F[b] / HW,  dG[c][d] = d_desc[b, l, (c/k)*g + d/k] / k^2.
- * dF: fp32, element (b,c,x) at dF[b*df_img_stride + c*df_row_stride + x*df_x_stride]; overwritten. F and dF must use
- * the same layout (both x contiguous or both c contiguous, see gh_gram_pool_fwd).
+ * dF: dtype df_dtype, element (b,c,x) at dF[b*df_img_stride + c*df_row_stride + x*df_x_stride]; overwritten. F and dF
+ * must use the same layout (both x contiguous or both c contiguous, see gh_gram_pool_fwd). df_dtype = GH_DTYPE_BF16
+ * writes the gradient as bf16 straight from the accumulators (half the bytes; what a bf16 backbone's backward
+ * consumes): CTA-pair kernels only, GH_ERR_UNSUPPORTED when they do not apply (then ask for fp32 and cast).
  * Requires C % g == 0, k a power of two, g <= 64, C % 16 == 0. */
 int gh_gram_pool_bwd(const void* F, int f_dtype, long long img_stride, long long row_stride, long long x_stride, int B,
-                     int C, int HW, int g, const float* d_desc, int l, int L, float* dF, long long df_img_stride,
-                     long long df_row_stride, long long df_x_stride, int max_ctas, void* stream);
+                     int C, int HW, int g, const float* d_desc, int l, int L, void* dF, int df_dtype,
+                     long long df_img_stride, long long df_row_stride, long long df_x_stride, int max_ctas, void* stream);
 
 /* Dense Gram, backward: dF[b] = (dG[b] + dG[b]^T) F[b] / HW with dG (B, C, C) fp32. Requires C % 16 == 0. */
 int gh_gram_dense_bwd(const void* F, int f_dtype, long long img_stride, long long row_stride, long long x_stride, int B,
-                      int C, int HW, const float* dG, float* dF, long long df_img_stride, long long df_row_stride,
-                      long long df_x_stride, int max_ctas, void* stream);
+                      int C, int HW, const float* dG, void* dF, int df_dtype, long long df_img_stride,
+                      long long df_row_stride, long long df_x_stride, int max_ctas, void* stream);
 
 /* Attention over the L stage descriptors + mean over stages + classifier, forward.  Replaces
  *   permute + self.attention(X, X, X) (nn.MultiheadAttention, 1 head): :56-58

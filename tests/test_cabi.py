@@ -40,7 +40,7 @@ def test_argument_validation_without_gpu(library):
     assert library.gh_gram_pool_fwd(None, 0, 0, 0, 1, 1, 256, 64, 32, None, 0, 1, 0, 0, None) == _lib.GH_ERR_BAD_ARG
     assert library.gh_gram_dense_fwd(None, 0, 0, 0, 1, 1, 256, 64, None, 0, 0, None) == _lib.GH_ERR_BAD_ARG
     assert library.gh_attn_head_fwd(*([None] * 7), 1, 3, 64, 4, *([None] * 5), None) == _lib.GH_ERR_BAD_ARG
-    assert library.gh_gram_pool_bwd(None, 0, 0, 0, 1, 1, 256, 64, 32, None, 0, 1, None, 0, 0, 1, 0, None) == _lib.GH_ERR_BAD_ARG
+    assert library.gh_gram_pool_bwd(None, 0, 0, 0, 1, 1, 256, 64, 32, None, 0, 1, None, 0, 0, 0, 1, 0, None) == _lib.GH_ERR_BAD_ARG
     dummy = ctypes.c_void_p(16)
     # non-power-of-two pooling factor and oversize g are refused before any launch
     assert library.gh_gram_pool_fwd(dummy, 0, 96 * 64, 64, 1, 1, 96, 64, 32, dummy, 0, 1, 0, 0, None) == _lib.GH_ERR_UNSUPPORTED

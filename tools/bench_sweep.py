@@ -1,7 +1,9 @@
 """BASELINE.json configs[4]: Gram kernel sweep across truncation depths and batch sizes against the measured rooflines.
 Kernel-only, features resident in HBM (relu(randn): ~50 % zeros like post-ReLU activations), CUDA events, >= 3 warm-ups,
-each timed loop touches > 126 MB (or is flagged "L2-resident"). Prints a markdown table; run on a B200:
-    python tools/bench_sweep.py > gpurun_out/sweep.md"""
+each timed loop touches > 126 MB (or is flagged "L2-resident"). Features are channels_last (NHWC) 4-D tensors, the layout
+the default backbone execution hands over (--nchw: (B, C, HW) rows, the reference's execution). Prints a markdown table;
+run on a B200:
+    python tools/bench_sweep.py [--nchw] > gpurun_out/sweep.md"""
 from __future__ import annotations
 
 import json
@@ -31,9 +33,13 @@ def main():
     pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.isfile(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
     hbm, tc = pk["hbm_gbs"], pk["bf16_tflops"]
     g = 32
-    shapes = [(256, 3136), (512, 784), (1024, 196), (2048, 49), (256, 12544), (512, 3136), (1024, 784)]
+    nchw = "--nchw" in sys.argv
+    shapes = [(256, 3136), (512, 784), (1024, 196), (2048, 49), (256, 12544), (512, 3136), (1024, 784), (2048, 196)]
     batches = [64, 128, 256, 512, 1024, 2048]
-    print(f"peaks: HBM {hbm} GB/s, bf16 {tc} TFLOP/s (burst: kernels timed alone), {torch.cuda.get_device_name(0)}\n")
+    print(f"peaks: HBM {hbm} GB/s, bf16 {tc} TFLOP/s (burst: kernels timed alone), {torch.cuda.get_device_name(0)}; "
+          f"features: {'NCHW rows (B, C, HW)' if nchw else 'channels_last (NHWC), the default hand-off'}; roofline us = "
+          "max(algorithmic bytes / HBM, algorithmic FLOPs / bf16 peak) -- fp32 features run on tf32 operands (half the bf16 "
+          "rate), so their 'frac of roofline' is against a peak that path cannot reach\n")
     print("| dir | dtype | C | HW | B | us | GB/s | of HBM | TFLOP/s (sym fwd / dense bwd) | of tensor | roofline us | frac of roofline | note |")
     print("|---|---|---|---|---|---|---|---|---|---|---|---|---|")
     for dtype in (torch.float32, torch.bfloat16):
@@ -43,6 +49,9 @@ def main():
                 if elems * 4 > 6e9 or (dtype is torch.bfloat16 and B not in (256, 1024)):
                     continue
                 x = torch.relu(torch.randn(B, C, HW, device="cuda")).to(dtype)
+                if not nchw:
+                    side = int(round(HW ** 0.5))
+                    x = x.view(B, C, side, side).contiguous(memory_format=torch.channels_last)
                 desc = torch.empty(B, 1, g * g, device="cuda")
                 dd = torch.randn(B, 1, g * g, device="cuda")
                 es = x.element_size()
