@@ -562,8 +562,10 @@ def run_ours(args):
         torch.manual_seed(0)
         tmodel = TruncatedResNet50(models.resnet50(weights=None), TRUNC, NUM_CLASSES, GRAM_SIZE, device=device)
         tmodel.train()
-        ddp = D.wrap_ddp(tmodel, device)
-        opt = torch.optim.AdamW(tmodel.parameters(), lr=1e-3)
+        # DDP settings from tools/sweep_ddp.py (profiles/r2_ddp_sweep_*.json): 16 MB buckets + static_graph start the
+        # all-reduce of the head's gradients (ready first) under the encoder's backward; fused AdamW is one launch
+        ddp = D.wrap_ddp(tmodel, device, bucket_cap_mb=16, static_graph=True)
+        opt = torch.optim.AdamW(tmodel.parameters(), lr=1e-3, fused=True)
         crit = torch.nn.CrossEntropyLoss()
         torch.manual_seed(100 + rank)
         xt = torch.randn(hi - lo, 3, IMAGE, IMAGE, device=device)
@@ -588,7 +590,8 @@ def run_ours(args):
                  "ms_per_step": round(tms / tsteps, 2), "steps": tsteps, "scaling": "strong",
                  "config": {"workload": "configs[2]: full training step (forward + Gram/attention backward + cuDNN "
                                         "backward + AdamW), train-mode BN, CE loss", "global_batch": gb,
-                            "per_gpu_batch": hi - lo, "optimizer": "AdamW(lr=1e-3)",
+                            "per_gpu_batch": hi - lo, "optimizer": "AdamW(lr=1e-3, fused=True)",
+                            "ddp": "bucket_cap_mb=16, static_graph=True, gradient_as_bucket_view=True, fp32 all-reduce" if world > 1 else None,
                             "parallelism": f"ddp{world}" if world > 1 else "single"},
                  "kernels": tk, "roofline": troof, "head": thead}
         if world == 1 and not args.skip_handoff:

@@ -496,6 +496,10 @@ def clear_weight_planes() -> None:
 
 def weight_planes(w: torch.Tensor) -> torch.Tensor:
     import weakref
+    if torch.cuda.is_current_stream_capturing():
+        # inside a CUDA-graph capture (e.g. a captured training step, where the weights change on every replay) the split
+        # must be part of the graph: never answer from -- or fill -- the cache
+        return split_bf16(w)
     key = id(w)
     hit = _WEIGHT_PLANES.get(key)
     if hit is not None:

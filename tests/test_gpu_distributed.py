@@ -24,7 +24,9 @@ def test_ddp_step_equals_single_gpu_step_on_the_concatenated_batch():
     line = [ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1]
     out = json.loads(line)
     assert out["world"] == 2 and out["backend"] == "nccl"
-    # fp32 sums in another order (two shard means averaged by the all-reduce vs one mean over the batch)
-    assert out["worst_head_grad_rel"] <= 1e-4, out
-    assert out["worst_grad_rel"] <= 2e-3, out
-    assert out["worst_weight_rel"] <= 1e-4, out
+    # fp32 sums in another order (two shard means averaged by the all-reduce vs one mean over the batch): the head's
+    # gradients agree to 1e-5 (measured 3e-6). In the encoder cuDNN picks other kernels for batch 4 than for batch 8, and
+    # the batch-norm bias gradients are sums over every position with heavy cancellation: 1e-2 there (measured 3e-3).
+    assert out["worst_head_grad_rel"] <= 1e-5, out
+    assert out["worst_grad_rel"] <= 1e-2, out
+    assert out["worst_weight_rel"] <= 1e-2, out       # zero-initialised BN biases after one step ARE their gradients

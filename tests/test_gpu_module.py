@@ -510,3 +510,41 @@ def test_whole_module_at_other_truncation_depths(trunc):
         e1, l1 = ours(x)
         e2, l2 = port(x)
     assert O.rel_err(npf(e1), npf(e2)) <= 1e-3 and torch.equal(l1.argmax(1), l2.argmax(1))
+
+
+def test_graphed_train_step_matches_the_eager_step():
+    """functions.GraphedTrainStep: the captured step (forward, CE loss, Gram / attention backward, cuDNN backward, AdamW)
+    replayed k times equals k eager steps from the same weights on the same batch -- up to the summation order of the
+    attention backward's reduce-adds -- and refuses DistributedDataParallel models."""
+    from torchvision import models
+    from heuristique_style_transfer_code_b200 import TruncatedResNet50
+    from heuristique_style_transfer_code_b200.functions import GraphedTrainStep
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(0)
+    a = TruncatedResNet50(models.resnet50(weights=None), 6, 4, 32, device="cuda").train()
+    b = TruncatedResNet50(models.resnet50(weights=None), 6, 4, 32, device="cuda").train()
+    b.load_state_dict(a.state_dict())
+    torch.manual_seed(1)
+    x = torch.randn(8, 3, 96, 96, device="cuda")
+    y = torch.randint(0, 4, (8,), device="cuda")
+    crit = torch.nn.CrossEntropyLoss()
+    oa = torch.optim.AdamW(a.parameters(), lr=1e-4, fused=True, capturable=True)
+    ob = torch.optim.AdamW(b.parameters(), lr=1e-4, fused=True)
+    warm, k = 3, 4
+    step = GraphedTrainStep(a, crit, oa, x, y, warmup=warm)
+    losses_a = [step().item() for _ in range(k)]
+    losses_b = []
+    for i in range(warm + k):
+        ob.zero_grad(set_to_none=True)
+        loss = crit(b(x), y)
+        loss.backward()
+        ob.step()
+        if i >= warm:
+            losses_b.append(loss.item())
+    assert np.allclose(losses_a, losses_b, rtol=2e-3, atol=1e-5), (losses_a, losses_b)
+    for (n, p), (_, q) in zip(a.named_parameters(), b.named_parameters()):
+        assert O.rel_err(npf(p), npf(q)) <= 2e-3, n
+    # new data goes through the captured buffers
+    x2 = torch.randn_like(x)
+    l2 = step(x2, y).item()
+    assert np.isfinite(l2) and abs(l2 - losses_a[-1]) > 0

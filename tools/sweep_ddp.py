@@ -90,7 +90,9 @@ def timeline(step, device, nsteps=3):
         torch.cuda.synchronize(device)
     nccl, compute, by_name = [], [], {}
     for ev in prof.events():
-        if ev.device_type != torch.autograd.DeviceType.CUDA:
+        if ev.device_type != torch.autograd.DeviceType.CUDA or getattr(ev, "is_user_annotation", False):
+            continue
+        if ev.name.startswith(("DistributedDataParallel", "autograd::", "Optimizer.", "ProfilerStep")):
             continue
         s, d = ev.time_range.start, ev.time_range.end - ev.time_range.start
         if d <= 0:
