@@ -85,8 +85,11 @@ class _TruncatedGramAttentionBase(nn.Module):
         return ops.gram_matrix(activations)
 
     def train(self, mode: bool = True):
-        if mode:
-            self._plan = None              # weights are about to change: the folded copies are rebuilt at the next eval
+        # Weights are about to change (train) or have just changed (eval after training): the folded encoder copies and the
+        # cached split planes of the attention weights are rebuilt at the next inference forward. Version counters alone
+        # cannot be trusted for this -- fused optimizers update parameters without bumping them.
+        self._plan = None
+        ops.clear_weight_planes()
         return super().train(mode)
 
     def refresh_inference_plan(self):
@@ -97,7 +100,11 @@ class _TruncatedGramAttentionBase(nn.Module):
 
     def _inference_plan(self, x):
         """The folded encoder when it computes the same function as the children (see frozen_encoder.py), else None."""
-        if not (self.fold_batchnorm and self._backbone_mode.endswith("channels_last")) or torch.is_grad_enabled():
+        if torch.is_grad_enabled():
+            if self._plan is not None and any(p.requires_grad for p in self.truncated_encoder.parameters()):
+                self._plan = None          # a gradient-enabled forward over trainable weights: an update may follow
+            return None
+        if not (self.fold_batchnorm and self._backbone_mode.endswith("channels_last")):
             return None
         enc = self.truncated_encoder
         if not x.is_cuda or any(m.training for m in enc.modules() if isinstance(m, nn.modules.batchnorm._BatchNorm)):

@@ -484,9 +484,15 @@ def split_bf16(x: torch.Tensor) -> torch.Tensor:
     return planes
 
 
-# Split planes of the attention weights, one entry per parameter object, rebuilt when the parameter's version counter or
-# storage changes (optimizer steps, load_state_dict, .to()). Edits through `.data` bypass the counter: call
-# clear_weight_planes() after them.
+# Split planes of the attention weights, cached per parameter object FOR INFERENCE ONLY.
+# Invalidation cannot rest on tensor version counters alone: fused optimizers (torch.optim.AdamW(fused=True), the default
+# of bench.py's training leg) update parameters without bumping `_version`. So:
+#   * a forward that may be followed by an update -- autograd enabled and the weight requires grad -- or that is being
+#     captured in a CUDA graph always splits afresh and evicts the weight's cache entry;
+#   * the modules clear the cache on every train() / eval() switch (modules.py);
+#   * otherwise an entry is valid while the parameter object, its storage address and its version counter are unchanged
+#     (load_state_dict, .to(), in-place edits, non-fused optimizers). Edits through `.data` bypass all of this: call
+#     clear_weight_planes() after them.
 _WEIGHT_PLANES = {}
 
 
@@ -496,11 +502,10 @@ def clear_weight_planes() -> None:
 
 def weight_planes(w: torch.Tensor) -> torch.Tensor:
     import weakref
-    if torch.cuda.is_current_stream_capturing():
-        # inside a CUDA-graph capture (e.g. a captured training step, where the weights change on every replay) the split
-        # must be part of the graph: never answer from -- or fill -- the cache
-        return split_bf16(w)
     key = id(w)
+    if torch.cuda.is_current_stream_capturing() or (torch.is_grad_enabled() and w.requires_grad):
+        _WEIGHT_PLANES.pop(key, None)
+        return split_bf16(w)
     hit = _WEIGHT_PLANES.get(key)
     if hit is not None:
         ref, version, ptr, planes = hit
