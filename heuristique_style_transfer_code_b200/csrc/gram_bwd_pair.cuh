@@ -14,7 +14,8 @@
 //   D = dF  [128 c][NT x]  per CTA in TMEM, two accumulator buffers: the epilogue of unit i overlaps the MMAs of i+1
 //   epilogue: tcgen05.ld (lane = channel, 32 positions) -> *scale -> swizzled staging tile -> TMA store, so the
 //             4 B/element gradient leaves the SM as full 128 B lines without occupying the LSU
-// Warps: 0 and 22 = TMA producers (even / odd K chunks), 1 = TMEM owner + MMA issuer (leader CTA only), 2-5 = epilogue,
+// Warps: 0 and 22 = TMA producers (even / odd K chunks), 1 = TMEM owner + MMA issuer (leader CTA only), 2-5 and 23-26 =
+// epilogue (two sets of four: even / odd 32-column chunks),
 // 6-21 = A-tile generators in four groups of four warps; group i generates the K chunks n = i mod 4 (into A-ring stage
 // n mod 5), so four chunks are generated concurrently and the per-chunk handshake (mbarrier wait, proxy fence, arrive)
 // of one group overlaps the stores of the others. A and B tiles travel in separate rings: 5 stages of generated A, 5 stages (80 KB) of TMA-loaded F, 3 store
@@ -31,20 +32,23 @@ namespace gh {
 // arrive, well under a microsecond), the F tiles come from HBM / L2 with 1-2 us of loaded latency: bytes in flight =
 // bandwidth x latency, so the B ring is as deep as shared memory allows and the A ring only as deep as it must be.
 #ifndef GH_BP_STORE_BUFS
-#define GH_BP_STORE_BUFS 3
+#define GH_BP_STORE_BUFS 2
 #endif
-// Ring depths are launch parameters (GramBwdPairParams::a_stages / b_stages, a_stages + b_stages <= kBpRingTiles): the
-// HBM-bound C = 256 stage is fastest with 5 + 5 (a deeper F ring is 20 % slower there), the C >= 512 stages -- whose F
-// tiles come mostly from L2 and whose generated A chunks shrink with the pooling factor -- want the F ring as deep as
-// shared memory allows (bytes in flight = bandwidth x latency).
+// Ring depths are launch parameters (GramBwdPairParams::a_stages / b_stages): a_stages A tiles of 16 KB and as many F
+// stages of b_stage_bytes (the x-tile width decides) as fit in the remaining kBpRingTiles - a_stages tiles. The F tiles
+// of the C >= 512 stages come mostly from L2 and want the ring as deep as shared memory allows (bytes in flight =
+// bandwidth x latency). Measured and rejected (profiles/r2_gram_bwd_experiments.md): ONE ring with a single full / empty
+// barrier pair per slot (halves the MMA issuer's waits and commits per chunk, but leaves only 4-5 slots: 5-17 % slower).
 // a_stages >= kBpGroups: generator group i produces the chunks n = i (mod 4); its next chunk n + 4 reuses the stage of
 // chunk n + 4 - a_stages, which must be a chunk this group (or an earlier one) has already PUBLISHED -- otherwise its
 // wait on the stage's `empty` barrier could run two phases ahead of the barrier and pass on the aliased parity.
-constexpr int kBpRingTiles = 10;                            // A stages + B stages
+constexpr int kBpRingTiles = 9;                             // A stages + F tiles, in 16 KB tiles
 constexpr int kBpMaxStages = 12;                            // per ring (sizes the barrier arrays)
 constexpr uint32_t kBpTileBytes = 16384;                    // A: [128 c][128 B]; B: <= 128 x-columns x (K chunk) x elem
 constexpr int kBpStoreBufs = GH_BP_STORE_BUFS;              // staging tiles per epilogue warp = TMA stores it keeps in flight
-constexpr uint32_t kBpStoreBytes = 4 * kBpStoreBufs * 4096; // per epilogue warp: kBpStoreBufs [32 c][32 x] fp32 staging tiles
+constexpr int kBpEpiWarps = 8;                              // two sets of four (one warp per TMEM lane quarter): set s drains
+                                                            // the 32-column chunks s, s + 2, ... of a unit's accumulator
+constexpr uint32_t kBpStoreBytes = kBpEpiWarps * kBpStoreBufs * 4096; // per epilogue warp: kBpStoreBufs [32 c][32 x] fp32 staging tiles
 constexpr int kBpMaxG = 32;                                 // pooled size handled here (larger g: the ldg kernels)
 constexpr int kBpGroups = 4;                                // generator groups (four warps each); group i generates chunks n = i mod 4
 constexpr int kBpTableFloats = kBpMaxG * kBpMaxG + kBpMaxG; // g x g table + one row of zeros (rows beyond C)
@@ -52,8 +56,9 @@ constexpr uint32_t kBpSymBytes = 2 * kBpTableFloats * 4;    // current and next 
 constexpr uint32_t kBpSmemBytes = kBpRingTiles * kBpTileBytes + kBpStoreBytes + kBpSymBytes + 1024 + 512;
 constexpr int kBpGroupThreads = 128;                        // one thread per A row
 constexpr int kBpGenThreads = kBpGroups * kBpGroupThreads;
-constexpr int kBpProducer2Warp = 6 + kBpGenThreads / 32;    // second TMA producer warp (the last one)
-constexpr int kBpThreads = (kBpProducer2Warp + 1) * 32;
+constexpr int kBpProducer2Warp = 6 + kBpGenThreads / 32;    // second TMA producer warp
+constexpr int kBpEpi2Warp0 = kBpProducer2Warp + 1;          // second set of epilogue warps: 23..26 (23 & 3 = 3, 24 & 3 = 0, ...)
+constexpr int kBpThreads = (kBpEpi2Warp0 + 4) * 32;
 static_assert(kBpSmemBytes <= 232448, "gram_bwd_pair: shared memory budget");
 
 struct GramBwdPairParams {
@@ -145,7 +150,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 8);                            // 4 epilogue warps x 2 CTAs
+      mbar_init(bar_tempty + 8 * a, 2 * kBpEpiWarps);              // 8 epilogue warps x 2 CTAs
     }
     mbar_fence_init();
   }
@@ -241,10 +246,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
       }
     }
     __syncwarp();
-  } else if (warp < 6) {
+  } else if (warp < 6 || warp >= kBpEpi2Warp0) {
     // =========================== epilogue: TMEM -> scale -> staging -> TMA store ===========================
+    // Eight warps: with four, draining a 128 x 160 accumulator took about as long as the 5 120 cycles of MMAs of a
+    // C = 512 unit and the tensor pipe idled 40 % of the time (profiles/r2_bwd512_ncu_summary.txt).
     const int q = warp & 3;                                 // TMEM lane quarter this warp may read
-    const uint32_t my_store = store_smem + (uint32_t)(warp - 2) * (kBpStoreBufs * 4096u);
+    const int eset = warp < 6 ? 0 : 1;                      // which half of the 32-column chunks
+    const int eidx = warp < 6 ? warp - 2 : 4 + (warp - kBpEpi2Warp0);
+    const uint32_t my_store = store_smem + (uint32_t)eidx * (kBpStoreBufs * 4096u);
     uint32_t it = 0, buf = 0;
     for (int u = u_begin; u < u_end; ++u, ++it) {
       const GramBwdPairUnit w = gbp_decode(p, u);
@@ -254,7 +263,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256u;
       const int crow0 = w.cb * 256 + (int)rank * 128 + q * 32;
 #pragma unroll 1
-      for (int n0 = 0; n0 < p.NT; n0 += 32) {
+      for (int n0 = 32 * eset; n0 < p.NT; n0 += 64) {
         const int x = w.ht * p.NT + n0;
         if (x >= p.HW) break;                               // warp-uniform
         float v[32];

@@ -299,10 +299,9 @@ static int gram_bwd_common(const void* F, int f_dtype, long long img_stride, lon
       q.dP = dP; q.dp_img_stride = dp_img_stride; q.g = g; q.kshift = p.kshift; q.dG = dG;
       q.scale = p.scale;
       q.df_bf16 = df16 ? 1 : 0;
-      // ring depths: see gram_bwd_pair.cuh. C = 256 is HBM-bound and fastest at 5 + 5; wider stages re-read F from L2
-      // and are bound by the bytes the F ring keeps in flight.
-      q.a_stages = 5; q.b_stages = 5;
-      if (C >= 512) { q.a_stages = 4; q.b_stages = kBpMaxStages; }
+      // ring depths: see gram_bwd_pair.cuh. Four A stages (the generator groups need that many; the generated chunks are
+      // cheap), the remaining tiles cut into F stages of the width the x tile needs.
+      q.a_stages = 4; q.b_stages = kBpMaxStages;
       if (g_opt_bwd_stages) { q.a_stages = g_opt_bwd_stages >> 4; q.b_stages = g_opt_bwd_stages & 15; }
       {   // one F stage: NHWC [NT/2 position rows][128 B]; NCHW: ceil(NT/2 / KC) x-blocks of [KC k-rows][128 B]
         const int half = q.NT / 2;
@@ -312,6 +311,7 @@ static int gram_bwd_common(const void* F, int f_dtype, long long img_stride, lon
         const long long fit = ((long long)(kBpRingTiles - q.a_stages) * kBpTileBytes) / sb;
         if (q.b_stages > fit) q.b_stages = (int)fit;
         if (q.b_stages > kBpMaxStages) q.b_stages = kBpMaxStages;
+        if (q.b_stages < 2) return GH_ERR_UNSUPPORTED;
       }
       q.nCB = (C + 255) / 256;
       q.nkc = (C + kc_elems - 1) / kc_elems;
@@ -503,7 +503,7 @@ int gh_set_option(const char* name, int value) {
     g_opt_bwd_nt = value;
     return 0;
   }
-  if (key == "gram_bwd_stages") {
+  if (key == "gram_bwd_stages") {        // value = a_stages * 16 + b_stages (experiments; b is capped by what fits)
     const int a = value >> 4, b = value & 15;
     if (value != 0 && (a < kBpGroups || b < 2 || a > kBpRingTiles - 2 || b > kBpMaxStages)) return GH_ERR_BAD_ARG;
     g_opt_bwd_stages = value;

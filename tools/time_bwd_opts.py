@@ -33,7 +33,7 @@ def main():
             x = torch.relu(torch.randn(B, C, side, side, device="cuda")).to(dtype).contiguous(memory_format=torch.channels_last)
             dd = torch.randn(B, 1, g * g, device="cuda")
             row = [f"{str(dtype)[6:]} C={C} HW={side * side}:"]
-            for a, b in ((5, 5), (5, 12), (4, 6), (4, 12), (6, 12)):
+            for a, b in ((4, 12), (5, 12)):
                 assert lib.gh_set_option(b"gram_bwd_stages", a * 16 + b) == 0
                 row.append(f"A{a}/B{b} {timeit(lambda: ops.gram_pool_bwd(x, g, dd, 0)):.1f}")
             lib.gh_set_option(b"gram_bwd_stages", 0)
