@@ -568,6 +568,7 @@ def test_training_steps_with_a_fused_optimizer_track_the_reference_port():
     y = torch.randint(0, 4, (8,), device="cuda")
     with torch.no_grad():                                 # an inference forward BEFORE training fills the caches
         ours(x)
+        port(x)                                           # (train-mode batch norm: keeps the running statistics in step)
     o1 = torch.optim.AdamW(ours.parameters(), lr=3e-4, fused=True)
     o2 = torch.optim.AdamW(port.parameters(), lr=3e-4, fused=True)
     for step in range(4):
