@@ -88,8 +88,11 @@ class _TruncatedGramAttentionBase(nn.Module):
         # Weights are about to change (train) or have just changed (eval after training): the folded encoder copies and the
         # cached split planes of the attention weights are rebuilt at the next inference forward. Version counters alone
         # cannot be trusted for this -- fused optimizers update parameters without bumping them.
-        self._plan = None
-        ops.clear_weight_planes()
+        # A call that changes nothing (eval() on a model already in eval mode) keeps them: captured CUDA graphs
+        # (streaming.CameraPipeline) hold the addresses of the folded tensors.
+        if mode or self.training != mode:
+            self._plan = None
+            ops.clear_weight_planes()
         return super().train(mode)
 
     def refresh_inference_plan(self):

@@ -146,6 +146,9 @@ class CameraPipeline:
                 with torch.cuda.graph(graph):
                     self._body()
                 self._graph = graph
+                # the graph holds raw addresses of the model's folded inference plan: keep that plan (and its tensors)
+                # alive for as long as this pipeline exists, whatever the model does with its own reference later
+                self._captured_plan = getattr(model, "_plan", None)
 
     # the device-side work for one frame; captured into the graph
     def preprocess_(self):
