@@ -15,7 +15,7 @@
 //   operands  = cp.async.bulk.tensor straight from the bf16 planes, either K-major ([rows][64 k], box 64 x rows) or
 //               MN-major ([64 k][64 mn] atoms through one 4-D box): the same planes serve X W^T (K-major weights), dY W
 //               (MN-major weights) and dY^T X (both MN-major) without any transposed copy
-//   ring      = 3 stages x {A_hi, A_lo, B_hi, B_lo} x 16 KB per CTA
+//   ring      = 3 stages x {A_hi, A_lo, B_hi, B_lo} x 16 KB per CTA (64 k per stage; GH_TG_KB=32: 6 x 4 x 8 KB)
 //   D         = two 256-column TMEM accumulators per CTA: the epilogue of unit i overlaps the MMAs of unit i+1
 //   epilogue  = tcgen05.ld -> (+ bias) -> swizzled staging tile -> TMA store (fp32), TMA reduce-add (fp32, K split) or
 //               TMA store of the hi / lo bf16 planes of the result (when the consumer is another GEMM of this kind)
@@ -26,9 +26,27 @@
 
 namespace gh {
 
-constexpr int kTgStages = 3;
-constexpr uint32_t kTgTile = 16384;                          // [128 rows][128 B] (or 2 MN-major atoms of [64 k][128 B])
+// K per stage: 64 (three stages of 64 KB per CTA; K-major tiles [rows][128 B], 128 B swizzle) or, with -DGH_TG_KB=32, 32
+// (six stages of 32 KB; K-major tiles [rows][64 B] with the 64 B swizzle; MN-major tiles [atom][32 k][128 B]). The deeper
+// ring keeps 160 KB instead of 128 KB per SM in flight; measured on B200 at batch 512 it changes nothing that matters
+// (attention forward 57.8 vs 59.4 us, backward 94.2 vs 90.1 us, gpurun_out r2s): with one 256 x 256 unit per CTA pair the
+// in_proj GEMM is bounded by its exposed prologue + pipeline fill + epilogue (CTA lifetime 51 k cycles for 24.6 k cycles of
+// MMAs), not by bytes in flight. Both settings pass the parity tests.
+#ifndef GH_TG_KB
+#define GH_TG_KB 64
+#endif
+constexpr int kTgKB = GH_TG_KB;
+static_assert(kTgKB == 32 || kTgKB == 64, "tgemm_pair: K block of 32 or 64");
+constexpr int kTgStages = kTgKB == 64 ? 3 : 6;
+constexpr uint32_t kTgRowB = kTgKB * 2;                      // bytes of one K-major row: 128 | 64
+constexpr uint32_t kTgTile = 128 * kTgRowB;                  // [128 rows][row] (or 2 MN-major atoms of [KB k][128 B]): 16 | 8 KB
 constexpr uint32_t kTgStageBytes = 4 * kTgTile;              // A_hi | A_lo | B_hi | B_lo, this CTA's halves
+constexpr uint32_t kTgKSteps = kTgKB / 16;                   // MMAs (x3) per stage: 4 | 2
+// K-major operand descriptor: 8-row groups of kTgRowB bytes; SWIZZLE_128B (layout 2) or SWIZZLE_64B (layout 4)
+__host__ __device__ constexpr uint64_t tg_desc_kmajor(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)((8u * kTgRowB) >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)(kTgKB == 64 ? 2 : 4) << 61);
+}
 constexpr int kTgStoreBufs = 2;                              // staging tiles per epilogue warp
 constexpr uint32_t kTgStoreBytes = 4 * kTgStoreBufs * 4096;
 constexpr uint32_t kTgSmemBytes = kTgStages * kTgStageBytes + kTgStoreBytes + 1024 + 256;
@@ -139,7 +157,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTgThreads, 1)
         const CUtensorMap* ma = &maps.a[w.pi];
         const CUtensorMap* mb = &maps.b[w.pi];
         const int half = q.tn >> 1;
-        const uint32_t tx_bytes = 2u * (2u * kTgTile + 2u * (uint32_t)half * kRowBytes);
+        const uint32_t tx_bytes = 2u * (2u * kTgTile + 2u * (uint32_t)half * kTgRowB);
         const int rowA = w.m0 + (int)rank * 128, rowB = w.n0 + (int)rank * half;
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1u, 100u + stage);
@@ -148,10 +166,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTgThreads, 1)
           const uint32_t fb = full_leader + 8 * stage;
 #pragma unroll
           for (int pl = 0; pl < 2; ++pl) {
-            if (q.a_mn) tma_load_4d_pair(st + pl * kTgTile, ma, fb, 0, kb * 64, rowA >> 6, pl);
-            else tma_load_3d_pair(st + pl * kTgTile, ma, fb, kb * 64, rowA, pl);
-            if (q.b_mn) tma_load_4d_pair(st + (2 + pl) * kTgTile, mb, fb, 0, kb * 64, rowB >> 6, pl);
-            else tma_load_3d_pair(st + (2 + pl) * kTgTile, mb, fb, kb * 64, rowB, pl);
+            if (q.a_mn) tma_load_4d_pair(st + pl * kTgTile, ma, fb, 0, kb * kTgKB, rowA >> 6, pl);
+            else tma_load_3d_pair(st + pl * kTgTile, ma, fb, kb * kTgKB, rowA, pl);
+            if (q.b_mn) tma_load_4d_pair(st + (2 + pl) * kTgTile, mb, fb, 0, kb * kTgKB, rowB >> 6, pl);
+            else tma_load_3d_pair(st + (2 + pl) * kTgTile, mb, fb, kb * kTgKB, rowB, pl);
           }
           if (++stage == kTgStages) { stage = 0; phase ^= 1u; }
         }
@@ -168,9 +186,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTgThreads, 1)
         const TgProblem& q = p.prob[w.pi];
         const uint32_t idesc = make_idesc(1u, 256u, (uint32_t)q.tn, (uint32_t)q.a_mn, (uint32_t)q.b_mn);
         // K-major tiles advance 32 B inside the 128 B row per MMA, MN-major ones by 16 k-rows of 128 B
-        const uint64_t dA0 = q.a_mn ? make_smem_desc_sw128_mnmajor(smem_base, 8192u) : make_smem_desc_sw128(smem_base);
-        const uint64_t dB0 = q.b_mn ? make_smem_desc_sw128_mnmajor(smem_base + 2 * kTgTile, 8192u)
-                                    : make_smem_desc_sw128(smem_base + 2 * kTgTile);
+        const uint64_t dA0 = q.a_mn ? make_smem_desc_sw128_mnmajor(smem_base, kTgKB * 128u) : tg_desc_kmajor(smem_base);
+        const uint64_t dB0 = q.b_mn ? make_smem_desc_sw128_mnmajor(smem_base + 2 * kTgTile, kTgKB * 128u)
+                                    : tg_desc_kmajor(smem_base + 2 * kTgTile);
         const uint64_t kAInc = q.a_mn ? 128u : 2u, kBInc = q.b_mn ? 128u : 2u;
         const uint32_t ab = it & 1u, use = it >> 1;
         mbar_wait_cl(bar_tempty + 8 * ab, (use & 1u) ^ 1u, 200u + ab);
@@ -182,7 +200,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTgThreads, 1)
           const uint64_t ah = dA0 + stage * kStageInc, al = ah + kTileInc;
           const uint64_t bh = dB0 + stage * kStageInc, bl = bh + kTileInc;
 #pragma unroll
-          for (uint32_t ks = 0; ks < 4; ++ks) {
+          for (uint32_t ks = 0; ks < kTgKSteps; ++ks) {
             // small terms first, then the dominant hi*hi
             umma2<KIND_BF16>(acc, al + ks * kAInc, bh + ks * kBInc, idesc, (kb != w.kb0 || ks != 0) ? 1u : 0u);
             umma2<KIND_BF16>(acc, ah + ks * kAInc, bl + ks * kBInc, idesc, 1u);
@@ -318,16 +336,16 @@ inline bool tg_map_operand(CUtensorMap* map, const TgOperand& o, int rows, int K
   if (!o.mn_major) {
     cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, 2};
     cuuint64_t strides[2] = {(cuuint64_t)(o.ld * 2), (cuuint64_t)(o.plane_stride * 2)};
-    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+    cuuint32_t box[3] = {(cuuint32_t)kTgKB, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(o.planes), dims, strides, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, kTgKB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
   }
   if (rows % 64 != 0 || box_rows % 64 != 0) return false;
   cuuint64_t dims[4] = {64, (cuuint64_t)K, (cuuint64_t)(rows / 64), 2};
   cuuint64_t strides[3] = {(cuuint64_t)(o.ld * 2), 128, (cuuint64_t)(o.plane_stride * 2)};
-  cuuint32_t box[4] = {64, 64, (cuuint32_t)(box_rows / 64), 1};
+  cuuint32_t box[4] = {64, (cuuint32_t)kTgKB, (cuuint32_t)(box_rows / 64), 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(o.planes), dims, strides, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -368,7 +386,7 @@ inline void tg_plan(TgSpec* specs, int n, int npairs) {
     double longest = 0;
     for (int i = 0; i < n; ++i) {
       const TgSpec& s = specs[i];
-      const int nkb = (s.K + 63) / 64;
+      const int nkb = (s.K + kTgKB - 1) / kTgKB;
       double pick_cost = -1;
       int pick_tn = 256, pick_ks = 1;
       double fallback_cost = 1e30;        // nothing fits under U: the shortest admissible unit
@@ -376,8 +394,8 @@ inline void tg_plan(TgSpec* specs, int n, int npairs) {
       for (int tn = 256; tn >= 128; tn >>= 1) {
         if (tn == 128 && s.N % 128 != 0 && s.N > 128) continue;
         for (int ks = 1; ks <= nkb && ks <= (s.max_split > 0 ? s.max_split : 1); ++ks) {
-          if (ks > 1 && nkb / ks < 2) break;
-          const double cost = (double)((nkb + ks - 1) / ks) * tn / 256.0;
+          if (ks > 1 && nkb / ks < 2 * (64 / kTgKB)) break;
+          const double cost = (double)((nkb + ks - 1) / ks) * tn / 256.0 * kTgKB / 64.0;
           // equal length: the unsplit (narrower) tiling wins -- no zeroed output, no reduce-add traffic
           if (cost <= U && (cost > pick_cost + 1e-9 || (cost > pick_cost - 1e-9 && ks < pick_ks))) {
             pick_cost = cost; pick_tn = tn; pick_ks = ks;
@@ -418,7 +436,7 @@ inline cudaError_t launch_tgemm(const TgSpec* specs, int n, int sms, cudaStream_
     TgProblem& q = p.prob[i];
     q.M = s.M; q.N = s.N; q.K = s.K;
     q.a_mn = s.A.mn_major; q.b_mn = s.B.mn_major;
-    q.tn = s.tn; q.tiles_n = (s.N + s.tn - 1) / s.tn; q.ksplit = s.ksplit; q.nkb = (s.K + 63) / 64;
+    q.tn = s.tn; q.tiles_n = (s.N + s.tn - 1) / s.tn; q.ksplit = s.ksplit; q.nkb = (s.K + kTgKB - 1) / kTgKB;
     q.unit0 = units;
     q.nunits = ((s.M + 255) / 256) * q.tiles_n * q.ksplit;
     units += q.nunits;
