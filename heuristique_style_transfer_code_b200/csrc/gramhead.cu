@@ -519,6 +519,11 @@ int gh_set_option(const char* name, int value) {
     g_opt_fwd_epilogue_warps = value;
     return 0;
   }
+  if (key == "tgemm_tn") {
+    if (value != 0 && value != 128 && value != 256) return GH_ERR_BAD_ARG;
+    g_opt_tg_tn = value;
+    return 0;
+  }
   if (key == "pdl") {
     if (value != 0 && value != 1) return GH_ERR_BAD_ARG;
     g_opt_pdl = value;

@@ -373,9 +373,12 @@ inline bool tg_map_out(CUtensorMap* map, const TgSpec& s) {
 }
 
 // Tile width and K partitions per problem. Cost model in units of one 256 x 256 x 64 k-block (12 MMAs, ~1 us):
-// a unit of `len` k-blocks at width tn costs len * tn/256 + 1.5 (pipeline fill + exposed epilogue); the launch takes
-// ceil(units / pairs) rounds of the longest unit. For every target unit length U the largest admissible unit <= U is
-// taken per problem, and the U with the smallest estimate wins.
+// a unit of `len` k-blocks at width tn costs len * tn/256 + 1.5 (pipeline fill + exposed epilogue); the launch takes ceil(units / pairs) rounds of the longest unit. For every
+// target unit length U the largest admissible unit <= U is taken per problem, and the U with the smallest estimate wins.
+// Measured against it on B200 (gpurun_out r2t, attention forward / backward at batch 512): forcing tn = 128 everywhere
+// 65.9 / 112.6 us, tn = 256 everywhere 72.1 / 122.9 us, this plan 59.4 / 90.1 us -- in particular two 128-wide units per
+// pair for the in_proj GEMM (to overlap one epilogue) lose to one 256-wide unit.
+static int g_opt_tg_tn = 0;            // 0 = plan; 128 / 256 force the tile width (experiments, gh_set_option "tgemm_tn")
 inline void tg_plan(TgSpec* specs, int n, int npairs) {
   static const int kTargets[] = {2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64, 96, 128, 192, 256};
   double best = 1e30;
@@ -393,6 +396,7 @@ inline void tg_plan(TgSpec* specs, int n, int npairs) {
       int fb_tn = 256, fb_ks = 1;
       for (int tn = 256; tn >= 128; tn >>= 1) {
         if (tn == 128 && s.N % 128 != 0 && s.N > 128) continue;
+        if (g_opt_tg_tn && tn != g_opt_tg_tn) continue;
         for (int ks = 1; ks <= nkb && ks <= (s.max_split > 0 ? s.max_split : 1); ++ks) {
           if (ks > 1 && nkb / ks < 2 * (64 / kTgKB)) break;
           const double cost = (double)((nkb + ks - 1) / ks) * tn / 256.0 * kTgKB / 64.0;

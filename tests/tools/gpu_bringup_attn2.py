@@ -166,6 +166,18 @@ def attn_small():
 
 
 @case
+def attn_tn():
+    """tile-width planning of tgemm_pair: forced 256, forced 128, planned"""
+    from heuristique_style_transfer_code_b200 import _lib
+    for tn in (256, 128, 0):
+        _lib.lib().gh_set_option(b"tgemm_tn", tn)
+        print("tgemm_tn =", tn)
+        _attn_case(512, 3, 32, 4, time_it=True)
+        _attn_case(256, 3, 32, 4, time_it=True)
+    _lib.lib().gh_set_option(b"tgemm_tn", 0)
+
+
+@case
 def attn_512():
     _attn_case(512, 3, 32, 4, time_it=True)
 
