@@ -32,12 +32,19 @@ int gh_version(void);
 /* Number of SMs the launchers size their persistent grids by (cudaDevAttrMultiProcessorCount of the current device). */
 int gh_sm_count(void);
 
-/* Launch tuning, process-wide. Known names: "gram_fwd_producer_warps" (0 = auto, 8, 16) and
- * "gram_fwd_epilogue_warps" (0 = auto, 4, 8); "gram_fwd_tma" (1 = TMA-staged operands for bf16 features whose
- * pitches are multiples of 16 B, 0 = always the ld.global producers; default 1); "gram_bwd_variant"
- * (1 = transposed product with gathered F^T tiles, 2 = F consumed as an MN-major operand, default 2); "gram_bwd_nhw"
- * (x-tile width of variant 2: 0 = auto, 128, 256); "gram_bwd_producer_warps" (8 or 16, for x-tile width 256); "attn_gemm" (1 = tcgen05 split-bf16 GEMMs for the attention linear
- * layers, 0 = fp32 FMA kernels; default 1). Unknown name or value outside the allowed set: GH_ERR_BAD_ARG. */
+/* Launch tuning, process-wide. Known names (unknown name or value outside the allowed set: GH_ERR_BAD_ARG):
+ *   "gram_fwd_pair", "gram_bwd_pair"   -1 = CTA-pair (TMA-staged) kernels whenever TMA can describe the tensors (default),
+ *                                      0 = never (ld.global-fed kernels), 1 = same as -1
+ *   "gram_fwd_producer_warps"          0 = auto, 8, 16        "gram_fwd_epilogue_warps"   0 = auto, 4, 8   (ld.global family)
+ *   "gram_bwd_variant"                 1 = transposed product with gathered F^T tiles, 2 = F as an MN-major operand (default)
+ *   "gram_bwd_nhw"                     x-tile width of variant 2: 0 = auto, 128, 256
+ *   "gram_bwd_producer_warps"          8 or 16 (variant 2, x-tile width 256)
+ *   "gram_bwd_nt"                      0 = plan the x-tile width of the pair backward; 64..256 (multiple of 16) forces it
+ *   "gram_bwd_stages"                  0 = by shape; a*16 + b = A / F ring depths of the pair backward (a >= 4)
+ *   "tma_f32_type"                     tensor-map type for fp32 features: 1 = TFLOAT32 (round to nearest, default), 0 = FLOAT32
+ *   "attn_gemm"                        ld.global attention family: 1 = tcgen05 split-bf16 GEMMs (default), 0 = fp32 FMA kernels
+ *   "tgemm_tn"                         tile width of the TMA-fed attention GEMMs: 0 = planned (default), 128, 256
+ *   "pdl"                              1 = programmatic dependent launch along the attention kernel chain (default), 0 = off */
 int gh_set_option(const char* name, int value);
 
 /* Reads and clears the error record {code, blockIdx.x, threadIdx.x, site} of the current device into host memory `out4`.
