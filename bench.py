@@ -40,6 +40,10 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# The training leg replays its step from a CUDA graph that contains DDP's NCCL all-reduce (functions.GraphedTrainStep):
+# torch requires NCCL's asynchronous error handling to be off for that, set before init_process_group.
+os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
+os.environ.setdefault("NCCL_ASYNC_ERROR_HANDLING", "0")
 
 import torch  # noqa: E402
 
@@ -562,10 +566,11 @@ def run_ours(args):
         torch.manual_seed(0)
         tmodel = TruncatedResNet50(models.resnet50(weights=None), TRUNC, NUM_CLASSES, GRAM_SIZE, device=device)
         tmodel.train()
-        # DDP settings from tools/sweep_ddp.py (profiles/r2_ddp_sweep_*.json): 16 MB buckets + static_graph start the
-        # all-reduce of the head's gradients (ready first) under the encoder's backward; fused AdamW is one launch
-        ddp = D.wrap_ddp(tmodel, device, bucket_cap_mb=16, static_graph=True)
-        opt = torch.optim.AdamW(tmodel.parameters(), lr=1e-3, fused=True)
+        # DDP settings from tools/sweep_ddp.py (profiles/r2_ddp_sweep_*.json): 16 MB buckets start the all-reduce of the
+        # head's gradients (ready first) under the encoder's backward; fused AdamW is one launch (capturable: the step is
+        # also replayed from a CUDA graph below); DDP is constructed on a side stream, as graph capture requires
+        ddp = D.wrap_ddp(tmodel, device, bucket_cap_mb=16, for_graph_capture=True)
+        opt = torch.optim.AdamW(tmodel.parameters(), lr=1e-3, fused=True, capturable=True)
         crit = torch.nn.CrossEntropyLoss()
         torch.manual_seed(100 + rank)
         xt = torch.randn(hi - lo, 3, IMAGE, IMAGE, device=device)
@@ -591,7 +596,7 @@ def run_ours(args):
                  "config": {"workload": "configs[2]: full training step (forward + Gram/attention backward + cuDNN "
                                         "backward + AdamW), train-mode BN, CE loss", "global_batch": gb,
                             "per_gpu_batch": hi - lo, "optimizer": "AdamW(lr=1e-3, fused=True)",
-                            "ddp": "bucket_cap_mb=16, static_graph=True, gradient_as_bucket_view=True, fp32 all-reduce" if world > 1 else None,
+                            "ddp": "bucket_cap_mb=16, gradient_as_bucket_view=True, fp32 all-reduce" if world > 1 else None,
                             "parallelism": f"ddp{world}" if world > 1 else "single"},
                  "kernels": tk, "roofline": troof, "head": thead}
         if world == 1 and not args.skip_handoff:
@@ -620,6 +625,28 @@ def run_ours(args):
             train["weak_scaling"] = {"value": round(gb * world * tsteps / (wms / 1e3), 1), "unit": "images/s",
                                      "ms_per_step": round(wms / tsteps, 2), "global_batch": gb * world,
                                      "per_gpu_batch": gb, "steps": tsteps, "scaling": "weak"}
+        # ---- the same step replayed from ONE CUDA graph (functions.GraphedTrainStep, the package's public API for fixed-shape
+        # training loops): forward, loss, backward, DDP's all-reduce and the fused AdamW update without a single host launch.
+        # At 64 images per GPU the eager step leaves the GPU idle ~15 % of the time (profiles/r2_ddp_sweep_timeline_8gpu.json).
+        # `value` of this leg is the replayed step; the eager measurement above stays beside it as `eager`.
+        if not args.no_graph_train:
+            from heuristique_style_transfer_code_b200.functions import GraphedTrainStep
+            if world > 1:
+                del xt, yt
+                torch.manual_seed(100 + rank)
+                xt = torch.randn(hi - lo, 3, IMAGE, IMAGE, device=device)
+                yt = torch.randint(0, NUM_CLASSES, (hi - lo,), device=device)
+            gstep = GraphedTrainStep(ddp, crit, opt, xt, yt, warmup=11)
+            for _ in range(3):
+                gstep()
+            gms = timed_region(lambda: gstep(), tsteps, device, D)
+            train["eager"] = {"value": train["value"], "ms_per_step": train["ms_per_step"]}
+            train["value"] = round(gb * tsteps / (gms / 1e3), 1)
+            train["ms_per_step"] = round(gms / tsteps, 2)
+            train["config"]["step"] = "replayed from one CUDA graph (GraphedTrainStep); `eager` = the same step launched kernel by kernel"
+            train["loss_after"] = float(gstep().item())
+            gstep.release()                         # before destroy_process_group: the graph holds NCCL work
+            del gstep
         del xt, yt, tmodel, ddp, opt
         torch.cuda.empty_cache()
 
@@ -678,6 +705,8 @@ def run_ours(args):
         key = "train_strong_img_s" if world > 1 else "train_img_s"
         line[key] = train["value"]
         line["train_ms_per_step"] = train["ms_per_step"]
+        if "eager" in train:
+            line[key.replace("img_s", "eager_img_s")] = train["eager"]["value"]
         if "weak_scaling" in train:
             line["train_weak_img_s"] = train["weak_scaling"]["value"]
         line["train_attn_fwd_us"] = th.get("attn_fwd_us")
@@ -728,6 +757,7 @@ def main():
     ap.add_argument("--skip-handoff", action="store_true")
     ap.add_argument("--skip-patchgan", action="store_true")
     ap.add_argument("--skip-reference-gpu", action="store_true")
+    ap.add_argument("--no-graph-train", action="store_true", help="training leg: eager step only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -115,7 +115,8 @@ def gather_rows(t: torch.Tensor, total_rows: int, world: int) -> torch.Tensor:
 
 
 def wrap_ddp(model: torch.nn.Module, device: torch.device, sync_bn: bool = False, bucket_cap_mb: int = 25,
-             broadcast_buffers: bool = True, static_graph: bool = False, grad_compression: str = "none") -> torch.nn.Module:
+             broadcast_buffers: bool = True, static_graph: bool = False, grad_compression: str = "none",
+             for_graph_capture: bool = False) -> torch.nn.Module:
     """DistributedDataParallel around the drop-in model (construct it with device=f'cuda:{local_rank}').
 
     bucket_cap_mb: gradient bucket size. The head's 16.8 MB of gradients are ready first in backward (attention and
@@ -124,15 +125,28 @@ def wrap_ddp(model: torch.nn.Module, device: torch.device, sync_bn: bool = False
     static_graph: the set of used parameters does not change between iterations (true for this model): DDP skips its
     per-iteration bookkeeping and may reorder buckets after the first step.
     grad_compression: "bf16" all-reduces bf16 copies of the gradient buckets (half the NVLink bytes; the averaged gradient
-    is rounded to bf16 once) -- opt-in, it changes the numerics of the update; "none" keeps fp32 (default)."""
+    is rounded to bf16 once) -- opt-in, it changes the numerics of the update; "none" keeps fp32 (default).
+    for_graph_capture: construct DDP on a side stream, as capturing its step in a CUDA graph requires."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return model
     if sync_bn:
         model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
     ids = [device.index] if device.type == "cuda" else None
-    ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=ids, bucket_cap_mb=bucket_cap_mb,
-                                                    broadcast_buffers=broadcast_buffers, gradient_as_bucket_view=True,
-                                                    static_graph=static_graph)
+
+    def build():
+        return torch.nn.parallel.DistributedDataParallel(model, device_ids=ids, bucket_cap_mb=bucket_cap_mb,
+                                                         broadcast_buffers=broadcast_buffers, gradient_as_bucket_view=True,
+                                                         static_graph=static_graph)
+    if for_graph_capture and device.type == "cuda":
+        # torch's rule for capturing a DDP step in a CUDA graph (functions.GraphedTrainStep): DDP is constructed on a side
+        # stream, and TORCH_NCCL_ASYNC_ERROR_HANDLING=0 must have been set before init_process_group
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            ddp = build()
+        torch.cuda.current_stream(device).wait_stream(side)
+    else:
+        ddp = build()
     if grad_compression == "bf16":
         from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
         ddp.register_comm_hook(None, default_hooks.bf16_compress_hook)

@@ -283,17 +283,17 @@ class GraphedTrainStep:
     removes the launches; the arithmetic and its order are the eager step's.
 
     Requirements: fixed batch shape (the example batch's); an optimizer that can be captured (torch.optim.AdamW / Adam with
-    capturable=True, SGD as it is). Single process only: capturing a DistributedDataParallel step (NCCL all-reduce inside
-    the graph) hung on the 2-GPU box it was tried on (round 2) and is refused here; on one GPU at batch 64 the replayed step
-    is 3 % faster than the eager one (14.45 vs 14.89 ms, tools/time_train_graph.py)."""
+    capturable=True, SGD as it is). `model` may be wrapped in DistributedDataParallel -- the NCCL all-reduce is then part of
+    the graph. For that, torch's rules for capturing DDP apply: TORCH_NCCL_ASYNC_ERROR_HANDLING=0 in the environment before
+    init_process_group, DDP constructed on a side stream (distributed.wrap_ddp(..., for_graph_capture=True)), at least 11
+    eager iterations before the capture (the default `warmup`), and the graph must be released before the process group is
+    destroyed (call release(); destroy_process_group() hangs otherwise). Measured: 64 images per GPU, 2 GPUs, 20.3 ms eager ->
+    14.7 ms replayed (tests/tools/try_ddp_graph.py); one GPU at batch 64: 14.89 -> 14.45 ms."""
 
-    def __init__(self, model, criterion, optimizer, example_inputs, example_labels, warmup=3):
+    def __init__(self, model, criterion, optimizer, example_inputs, example_labels, warmup=11):
         device = example_inputs.device
         if device.type != 'cuda':
             raise ValueError("GraphedTrainStep needs CUDA tensors")
-        if isinstance(model, torch.nn.parallel.DistributedDataParallel):
-            raise NotImplementedError("GraphedTrainStep: capturing a DistributedDataParallel step is not supported "
-                                      "(the NCCL all-reduce inside the capture hung in testing); use the eager step")
         self.model, self.criterion, self.optimizer = model, criterion, optimizer
         self.inputs = example_inputs.detach().clone()
         self.labels = example_labels.detach().clone()
@@ -318,6 +318,13 @@ class GraphedTrainStep:
     def _eager(self):
         self.optimizer.zero_grad(set_to_none=True)
         return self._forward_backward_step()
+
+    def release(self):
+        """Drops the captured graph (and the memory pool it owns). Required before torch.distributed.destroy_process_group()
+        when the captured step contains NCCL collectives."""
+        self.graph = None
+        self.loss = None
+        torch.cuda.synchronize(self.inputs.device)
 
     def __call__(self, inputs=None, labels=None):
         """Copies the batch into the captured buffers (skipped when None: the captured tensors are reused) and replays the

@@ -30,3 +30,18 @@ def test_ddp_step_equals_single_gpu_step_on_the_concatenated_batch():
     assert out["worst_head_grad_rel"] <= 1e-5, out
     assert out["worst_grad_rel"] <= 1e-2, out
     assert out["worst_weight_rel"] <= 1e-2, out       # zero-initialised BN biases after one step ARE their gradients
+
+
+def test_graphed_ddp_step_follows_the_eager_ddp_step():
+    """functions.GraphedTrainStep over a DistributedDataParallel model (2 ranks, NCCL all-reduce inside the CUDA graph):
+    the losses of the replayed steps follow the eager DDP steps from the same weights."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (one process per GPU over NCCL)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29732", os.path.join(ROOT, "tests", "tools", "ddp_worker.py"), "--graph"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    out = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith('{"graph_losses"')][-1])
+    assert len(out["graph_losses"]) == 3
+    for a, b in zip(out["graph_losses"], out["eager_losses"]):
+        assert abs(a - b) <= 2e-3 * abs(b), out

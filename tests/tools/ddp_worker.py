@@ -9,6 +9,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")      # required for capturing a DDP step in a CUDA graph
+os.environ.setdefault("NCCL_ASYNC_ERROR_HANDLING", "0")
 
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
@@ -80,6 +82,38 @@ def main():
         print(json.dumps({"world": world, "worst_grad_rel": worst_g, "worst_grad_name": worst_name,
                           "worst_head_grad_rel": head_g, "worst_weight_rel": worst_w,
                           "backend": dist.get_backend() if dist.is_initialized() else None}), flush=True)
+    if "--graph" in sys.argv:
+        # functions.GraphedTrainStep on a DDP model: the replayed step (NCCL all-reduce inside the graph) follows the eager
+        # DDP step from the same weights on the same shard
+        from heuristique_style_transfer_code_b200.functions import GraphedTrainStep
+        crit = torch.nn.CrossEntropyLoss()
+        losses = {}
+        warm, k = 11, 3
+        for kind in ("eager", "graph"):
+            m = build(device)
+            m.load_state_dict(model.state_dict())
+            ddp2 = D.wrap_ddp(m, device, bucket_cap_mb=16, for_graph_capture=True)
+            o = torch.optim.AdamW(m.parameters(), lr=1e-4, fused=True, capturable=True)
+            xs, ys = x[lo:hi].contiguous(), y[lo:hi].contiguous()
+            if kind == "graph":
+                step = GraphedTrainStep(ddp2, crit, o, xs, ys, warmup=warm)
+                losses[kind] = [step().item() for _ in range(k)]
+                step.release()
+                del step
+            else:
+                out = []
+                for i in range(warm + k):
+                    o.zero_grad(set_to_none=True)
+                    loss = crit(ddp2(xs), ys)
+                    loss.backward()
+                    o.step()
+                    if i >= warm:
+                        out.append(loss.item())
+                losses[kind] = out
+            del ddp2, o, m
+            torch.cuda.synchronize(device)
+        if rank == 0:
+            print(json.dumps({"graph_losses": losses["graph"], "eager_losses": losses["eager"]}), flush=True)
     if dist.is_initialized():
         dist.barrier(device_ids=[device.index])
         dist.destroy_process_group()
