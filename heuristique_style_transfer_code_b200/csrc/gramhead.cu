@@ -822,6 +822,17 @@ int gh_split_bf16(const float* src, void* planes, long long n, long long plane_s
                          (__nv_bfloat16*)planes, n4, plane_stride);
 }
 
+int gh_tgemm_plan(int M, int N, int K, int max_split, int npairs, int* tn, int* ksplit, int* units) {
+  if (M <= 0 || N <= 0 || K <= 0 || npairs <= 0 || !tn || !ksplit || !units) return GH_ERR_BAD_ARG;
+  TgSpec s{};
+  s.M = M; s.N = N; s.K = K; s.max_split = max_split < 1 ? 1 : max_split; s.tn = 256; s.ksplit = 1;
+  tg_plan(&s, 1, npairs);
+  *tn = s.tn;
+  *ksplit = s.ksplit;
+  *units = ((M + 255) / 256) * ((N + s.tn - 1) / s.tn) * s.ksplit;
+  return 0;
+}
+
 int gh_gemm_planes(const void* A_planes, long long lda, long long a_plane_stride, int a_mn, const void* B_planes,
                    long long ldb, long long b_plane_stride, int b_mn, const float* bias, float* D, void* D_planes,
                    long long ldd, long long d_plane_stride, int M, int N, int K, int max_split, void* stream) {

@@ -233,6 +233,10 @@ int gh_gemm_planes(const void* A_planes, long long lda, long long a_plane_stride
                    long long ldb, long long b_plane_stride, int b_mn, const float* bias, float* D, void* D_planes,
                    long long ldd, long long d_plane_stride, int M, int N, int K, int max_split, void* stream);
 
+/* Host-only: the tiling gh_gemm_planes / gh_attn_head_fwd2 / _bwd2 choose for one M x N x K problem on `npairs` CTA pairs
+ * (tile width 256 or 128, number of K partitions <= max_split, resulting work units). No GPU needed. */
+int gh_tgemm_plan(int M, int N, int K, int max_split, int npairs, int* tn, int* ksplit, int* units);
+
 /* Forward. w_in_planes: planes of in_proj_weight (2, 3E, E); w_out_planes: planes of out_proj.weight (2, E, E) (dense,
  * plane_stride = rows*E). b_in, b_out, W_c, b_c fp32 as in gh_attn_head_fwd. Outputs: emb (B, E), logits (B, nc); saved
  * for backward: x_planes (2, B*L, E) bf16, qkv (B*L, 3E) fp32, probs (B, L, L) fp32, obar_planes (2, B, E) bf16.

@@ -75,3 +75,31 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "_LIB", None)
     with pytest.raises(_lib.GramHeadError, match="no CPU or PyTorch fallback"):
         _lib.lib()
+
+
+def test_tgemm_planner_host_logic(library):
+    """gh_tgemm_plan (no GPU needed): the tiling of the attention GEMMs. The forward never splits K in more than two
+    partitions (bitwise reproducibility), big problems fill the 74 CTA pairs of a B200 in whole rounds, small ones are split
+    to use the machine, and a partition keeps at least two 64-wide k-blocks."""
+    import ctypes
+
+    def plan(M, N, K, max_split, pairs=74):
+        tn, ks, units = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        assert library.gh_tgemm_plan(M, N, K, max_split, pairs, ctypes.byref(tn), ctypes.byref(ks), ctypes.byref(units)) == 0
+        return tn.value, ks.value, units.value
+
+    # in_proj at batch 512 (B*L = 1536 rows): one 256 x 256 unit per pair, unsplit
+    assert plan(1536, 3072, 1024, 2) == (256, 1, 72)
+    # in_proj at batch 256: 36 wide tiles would leave half the pairs idle -> 72 narrow, unsplit units
+    tn, ks, units = plan(768, 3072, 1024, 2)
+    assert (tn, ks, units) == (128, 1, 72)
+    # out_proj (M = batch): forward limit of two partitions is respected
+    tn, ks, units = plan(512, 1024, 1024, 2)
+    assert ks <= 2 and tn in (128, 256) and units >= 16
+    # backward problems may split freely, but a partition keeps >= 2 k-blocks
+    for (M, N, K) in [(3072, 1024, 1536), (1536, 1024, 3072), (512, 1024, 1024), (1024, 1024, 512), (192, 1024, 3072)]:
+        tn, ks, units = plan(M, N, K, 64)
+        assert tn in (128, 256) and 1 <= ks <= (K + 63) // 64 // 2 and units == ((M + 255) // 256) * ((N + tn - 1) // tn) * ks
+    # tiny problems: a single unit, never more partitions than k-blocks allow
+    assert plan(8, 64, 64, 64) == (256, 1, 1) or plan(8, 64, 64, 64)[1] == 1
+    assert library.gh_tgemm_plan(0, 64, 64, 1, 74, None, None, None) == _lib.GH_ERR_BAD_ARG

@@ -302,3 +302,28 @@ def test_checkpoint_converters_produce_what_load_model_loads(tmp_path):
     ddp_like = {"module." + k: v for k, v in model.state_dict().items()}
     assert set(checkpoints.to_bare_encoder(ddp_like)) == set(checkpoints.to_bare_encoder(torch.load(three)))
     assert checkpoints.to_bare_encoder(converted).keys() == converted.keys()        # idempotent
+
+
+def test_reference_loader_restores_anomaly_mode_and_graphed_step_needs_cuda():
+    """_reference.load_reference_file: the reference files switch torch's anomaly detection on at import
+    (Models/...Attention.py:9); the loader must leave the caller's setting untouched. GraphedTrainStep is CUDA-only."""
+    import os
+    import pytest
+    import torch
+    from heuristique_style_transfer_code_b200 import _reference
+    from heuristique_style_transfer_code_b200.functions import GraphedTrainStep
+    rel = os.path.join("Models", "Models_RESNET50_TRUNCATE_GRAM_with_Attention.py")
+    if _reference.reference_root(rel) is None:
+        pytest.skip("no copy of the reference tree in this environment")
+    assert not torch.is_anomaly_enabled()
+    _reference._LOADED.pop(rel, None)
+    mod = _reference.load_reference_file(rel)
+    assert not torch.is_anomaly_enabled()
+    assert hasattr(mod, "TruncatedResNet50") and hasattr(mod, "TruncatedResNet50_for_test")
+    assert _reference.load_reference_file(rel) is mod                     # cached
+    with pytest.raises(NotImplementedError):
+        _reference.load_reference_file(os.path.join("Models", "does_not_exist.py"))
+    lin = torch.nn.Linear(4, 2)
+    with pytest.raises(ValueError):
+        GraphedTrainStep(lin, torch.nn.CrossEntropyLoss(), torch.optim.SGD(lin.parameters(), lr=0.1), torch.randn(3, 4),
+                         torch.zeros(3, dtype=torch.long))

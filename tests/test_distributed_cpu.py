@@ -79,3 +79,48 @@ def test_two_rank_gloo_sharded_inference_and_ddp():
         assert p.exitcode == 0
     ok_gather, ok_ddp, t = q.get(timeout=5)
     assert ok_gather and ok_ddp and t == 2.0
+
+
+def _ddp_options_worker(rank, world, port, out):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from heuristique_style_transfer_code_b200 import distributed as D
+    torch.manual_seed(0)
+    results = {}
+    for name, kw in (("plain", {}), ("static", dict(static_graph=True, bucket_cap_mb=1)),
+                     ("side_stream_flag", dict(for_graph_capture=True))):
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4))
+        ddp = D.wrap_ddp(net, torch.device("cpu"), **kw)
+        x = torch.arange(32, dtype=torch.float32).reshape(4, 8) / 10 + rank
+        ddp(x).square().mean().backward()
+        results[name] = torch.cat([p.grad.flatten() for p in net.parameters()])
+    try:
+        D.wrap_ddp(torch.nn.Linear(2, 2), torch.device("cpu"), grad_compression="fp8")
+        bad = False
+    except ValueError:
+        bad = True
+    if rank == 0:
+        out.put((results["plain"].tolist(), results["static"].tolist(), results["side_stream_flag"].tolist(), bad))
+    dist.destroy_process_group()
+
+
+def test_wrap_ddp_options_give_the_same_averaged_gradients():
+    """distributed.wrap_ddp on 2 gloo ranks: bucket size, static_graph and the graph-capture construction flag (a no-op
+    on CPU) do not change the averaged gradients; unknown compression names are refused."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29741
+    procs = [ctx.Process(target=_ddp_options_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    plain, static, flag, bad = out.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert plain == static == flag and bad
