@@ -126,18 +126,20 @@ def timed_region(fn, steps, device, dist_mod):
 
 
 HEAD_KINDS = ("gram_fwd", "gram_bwd", "attn")      # what the roofline object may name
+HEAD_TIME_KINDS = HEAD_KINDS + ("split",)          # + the per-step split of the attention weights into bf16 planes (training)
 
 
 def head_totals(records, steps, peaks):
     """Per-step time and algorithmic FLOPs of the head kernels (Gram forward: symmetric count C(C+1)HW; Gram backward:
-    dense 2 C^2 HW; attention: its GEMMs) and the fraction of the measured bf16 tensor peak they amount to."""
+    dense 2 C^2 HW; attention: its GEMMs; the weight-plane splits a training step needs count as attention-forward time,
+    with no FLOPs) and the fraction of the measured bf16 tensor peak they amount to."""
     t = {"gram_fwd": 0.0, "gram_bwd": 0.0, "attn_fwd": 0.0, "attn_bwd": 0.0}
     flops = 0.0
     for name, work, s, e in records:
         kind = work.get("kind")
-        if kind not in HEAD_KINDS:
+        if kind not in HEAD_TIME_KINDS:
             continue
-        key = kind if kind != "attn" else ("attn_bwd" if name.startswith("attn_head_bwd") else "attn_fwd")
+        key = kind if kind in ("gram_fwd", "gram_bwd") else ("attn_bwd" if name.startswith("attn_head_bwd") else "attn_fwd")
         t[key] += s.elapsed_time(e) * 1e3
         flops += work["flops"]
     total_us = sum(t.values()) / steps
