@@ -80,7 +80,27 @@ def lib() -> ctypes.CDLL:
             fn.restype = res
             fn.argtypes = args
         _LIB = handle
+        _apply_env_options(handle)
     return _LIB
+
+
+def _apply_env_options(handle) -> None:
+    """GRAMHEAD_OPTIONS="name=value,name=value": tuning knobs of gh_set_option (include/gramhead.h) for processes whose
+    code cannot be touched (the reference's unmodified scripts, profiler drivers). An unknown name or a rejected value
+    raises: a silently ignored knob would make a measurement lie."""
+    spec = os.environ.get("GRAMHEAD_OPTIONS", "").strip()
+    if not spec:
+        return
+    for item in spec.split(","):
+        name, sep, value = item.strip().partition("=")
+        if not sep or not name:
+            raise GramHeadError(f"gramhead: GRAMHEAD_OPTIONS: expected name=value, got {item!r}")
+        try:
+            ivalue = int(value)
+        except ValueError:
+            raise GramHeadError(f"gramhead: GRAMHEAD_OPTIONS: {name}: {value!r} is not an integer") from None
+        if handle.gh_set_option(name.encode(), ivalue) != 0:
+            raise GramHeadError(f"gramhead: GRAMHEAD_OPTIONS: gh_set_option({name!r}, {ivalue}) was rejected")
 
 
 def check(code: int, what: str) -> None:

@@ -71,7 +71,7 @@ struct GramBwdPairParams {
   float scale;
   int NT;                   // x-tile width of a pair (multiple of 32, <= 256); each CTA supplies NT/2 columns of B
   int nHT, nCB;             // x tiles, 256-channel output blocks
-  int nkc;                  // K chunks (32 input channels for tf32, 64 for bf16)
+  int nkc;                  // K stages per unit: CH chunks of 32 (tf32) / 64 (bf16) input channels each
   int total_units;
   int areuse;               // POOL: consecutive k-steps of a chunk whose A data is identical (1, 2 or 4), see below
   int a_stages, b_stages;   // ring depths (A: generated gradient tiles, B: TMA-loaded F tiles)
@@ -79,7 +79,26 @@ struct GramBwdPairParams {
                             // tiles the A ring leaves, cut into stages of the size the x-tile width needs
   int df_bf16;              // 1: dF leaves as bf16 (tmD is a bf16 map, 64 B swizzle): half the gradient bytes, and the
                             //    gradient a bf16 backbone wants; 0: fp32
+  int a_smem_tiles;         // 16 KB tiles the generated-A ring occupies in shared memory: a_stages, or 0 when the A
+                            // operand lives in tensor memory (ATS kernels: the whole ring then belongs to F)
+  int a_tmem_cols;          // ATS: TMEM columns of one A stage = CH * 32 / areuse (only the k-steps that differ are stored)
 };
+
+// -DGH_BP_PROFILE: per-role cycle accounting (clock64 around every mbarrier wait of one thread per role, summed over
+// the CTAs into g_bp_prof and read back by gh_bp_profile_read) -- where each warp role of the kernel spends its time.
+// Slots: 0 issuer loop, 1 issuer wait tmem_empty, 2 wait fullA, 3 wait fullB, 4 chunks issued, 5 epilogue (warp 2) loop,
+// 6 wait tmem_full, 7 wait staging tile, 8 generator (warp 6) loop, 9 wait emptyA, 10 producer (warp 0) loop,
+// 11 wait emptyB, 12 leader CTAs counted.
+#ifdef GH_BP_PROFILE
+__device__ unsigned long long g_bp_prof[16];
+#define GH_BP_CLK(var) const long long var = clock64()
+#define GH_BP_ADD(acc, var) acc += clock64() - var
+#define GH_BP_FLUSH(slot, acc) atomicAdd(&g_bp_prof[slot], (unsigned long long)(acc))
+#else
+#define GH_BP_CLK(var)
+#define GH_BP_ADD(acc, var)
+#define GH_BP_FLUSH(slot, acc)
+#endif
 
 struct GramBwdPairUnit {
   int b, ht, cb;
@@ -104,10 +123,24 @@ __device__ __forceinline__ uint32_t f32_to_tf32_rna(float x) {
 // NHWC = true : channels_last F and dF (c contiguous): F[d][x] at x*C + d is K-contiguous, i.e. a K-major B operand
 //               [NT/2 position rows][128 B of input channels] fetched by ONE box per chunk; the epilogue transposes
 //               through the staging tile ([32 x rows][32 channels]) so that dF is stored NHWC too.
-template <int KIND, int MODE, bool NHWC>
+// ATS  = true : (POOL only) the generated gradient tile is written to TENSOR MEMORY (tcgen05.st) and the MMAs take their
+//               A operand from there (UTCHMMA tmem, gdesc). Why: per unit the SS form moves through shared memory the A
+//               tile twice (generator stores + the tensor core's operand fetch, 4 KB per MMA and CTA whatever N is)
+//               on top of the F tiles (TMA write + operand fetch) and the gradient staging (write + TMA read) --
+//               872 KB per C = 512 unit against 5 120 cycles of MMAs, i.e. more than the ~90 B/clk the kernels of this
+//               library are seen to sustain; with A in TMEM it is 488 KB. Stage s of the A ring sits in the columns the
+//               two accumulators leave free: (s & 1) * 256 + NT + (s >> 1) * a_tmem_cols.
+// CH          : K chunks (128 B operand rows: 32 tf32 / 64 bf16 input channels) per ring stage. The single thread that
+//               issues the MMAs needs ~570 cycles per loop iteration (two mbarrier waits, descriptor arithmetic moved to
+//               uniform registers, 4 UTCHMMA, 2-3 UTCBAR -- measured with -DGH_BP_PROFILE: ~185 of them in waits that pass
+//               at once), while the four MMAs of a chunk execute in 320 (N = 160) to 448 cycles: with one chunk per
+//               stage the ISSUER paces the C >= 512 stages (tensor pipe 57 % active). CH = 2 (ATS only: a doubled A
+//               stage fits TMEM, not shared memory) issues eight MMAs per iteration.
+template <int KIND, int MODE, bool NHWC, bool ATS = false, int CH = 1>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
     gram_bwd_pair_kernel(const GramBwdPairParams p, const __grid_constant__ CUtensorMap tmF,
                          const __grid_constant__ CUtensorMap tmD) {
+  static_assert(CH == 1 || (CH == 2 && ATS), "a doubled stage needs the A operand in tensor memory");
   using T = KindTraits<KIND>;
   constexpr uint32_t KC = T::kElemsPerRow;                  // input channels per K chunk
   constexpr uint32_t kAtomBytesB = KC * kRowBytes;          // one 128 B-wide x block of the B tile: 4 KB | 8 KB
@@ -117,7 +150,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t kBpAStages = (uint32_t)p.a_stages, kBpBStages = (uint32_t)p.b_stages;   // launch parameters
   const uint32_t a_ring = smem_base;                                        // a_stages x 16 KB
-  const uint32_t b_ring = a_ring + kBpAStages * kBpTileBytes;               // b_stages x 16 KB
+  const uint32_t b_ring = a_ring + (uint32_t)p.a_smem_tiles * kBpTileBytes; // b_stages x b_stage_bytes
   const uint32_t store_smem = smem_base + kBpRingTiles * kBpTileBytes;
   const uint32_t sym_smem = store_smem + kBpStoreBytes;
   float* sym = reinterpret_cast<float*>(smem_raw + (sym_smem - smem_u32(smem_raw)));
@@ -175,25 +208,45 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
     const uint32_t pidx = (warp == 0) ? 0u : 1u;
     if (elected) {
       uint32_t n = 0;
-      const uint32_t tx_bytes = NHWC ? 2u * (uint32_t)(p.NT / 2) * kRowBytes : 2u * (uint32_t)na * kAtomBytesB;
+      [[maybe_unused]] long long prof_wait = 0;
+      GH_BP_CLK(prof_t0);
+      const uint32_t sub_tx = NHWC ? 2u * (uint32_t)(p.NT / 2) * kRowBytes : 2u * (uint32_t)na * kAtomBytesB;
+      const uint32_t sub_bytes = (uint32_t)p.b_stage_bytes / (uint32_t)CH;      // one chunk's F tile inside a stage
+      const int nsub_total = (p.C + (int)KC - 1) / (int)KC;                     // chunks that hold any channel < C
       for (int u = u_begin; u < u_end; ++u) {
         const GramBwdPairUnit w = gbp_decode(p, u);
         const int x0 = w.ht * p.NT + (int)rank * (p.NT / 2);
         for (int kc = 0; kc < p.nkc; ++kc, ++n) {
           if ((n & 1u) != pidx) continue;
           const uint32_t stage = n % (uint32_t)kBpBStages, phase = (n / (uint32_t)kBpBStages) & 1u;
+          GH_BP_CLK(prof_w);
           mbar_wait(bar_emptyB + 8 * stage, phase ^ 1u, 100u + stage);
-          if (rank == 0) mbar_arrive_expect_tx(bar_fullB + 8 * stage, tx_bytes);
-          const uint32_t b_tile = b_ring + stage * (uint32_t)p.b_stage_bytes;
-          if constexpr (NHWC) {
-            tma_load_3d_pair(b_tile, &tmF, fullB_leader + 8 * stage, kc * (int)KC, x0, w.b);
-          } else {
-            for (int j = 0; j < na; ++j)
-              tma_load_3d_pair(b_tile + (uint32_t)j * kAtomBytesB, &tmF, fullB_leader + 8 * stage, x0 + j * (int)KC,
-                               kc * (int)KC, w.b);
+          GH_BP_ADD(prof_wait, prof_w);
+          const int nsub = (kc * CH + CH <= nsub_total) ? CH : nsub_total - kc * CH;   // chunks of this stage in range
+          if (rank == 0) mbar_arrive_expect_tx(bar_fullB + 8 * stage, (uint32_t)nsub * sub_tx);
+#pragma unroll
+          for (int sc = 0; sc < CH; ++sc) {
+            if (sc >= nsub) break;
+            const uint32_t b_tile = b_ring + stage * (uint32_t)p.b_stage_bytes + (uint32_t)sc * sub_bytes;
+            const int ch0 = (kc * CH + sc) * (int)KC;
+            if constexpr (NHWC) {
+              tma_load_3d_pair(b_tile, &tmF, fullB_leader + 8 * stage, ch0, x0, w.b);
+            } else {
+              for (int j = 0; j < na; ++j)
+                tma_load_3d_pair(b_tile + (uint32_t)j * kAtomBytesB, &tmF, fullB_leader + 8 * stage, x0 + j * (int)KC, ch0,
+                                 w.b);
+            }
           }
         }
       }
+#ifdef GH_BP_PROFILE
+      if (warp == 0 && rank == 0) {
+        [[maybe_unused]] long long prof_tot = 0;
+        GH_BP_ADD(prof_tot, prof_t0);
+        GH_BP_FLUSH(10, prof_tot);
+        GH_BP_FLUSH(11, prof_wait);
+      }
+#endif
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -213,17 +266,53 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
       const int full_chunks = p.C / (int)KC;
       const uint32_t amask = (MODE == GRAM_POOL) ? (~((uint32_t)p.areuse - 1u) & 3u) : 3u;
       const uint64_t a1 = (1u & amask) * kAInc, a2 = (2u & amask) * kAInc, a3 = (3u & amask) * kAInc;
+      const uint32_t ashift = p.areuse >= 4 ? 2u : (p.areuse == 2 ? 1u : 0u);         // ATS: log2(areuse)
+      const uint32_t t1 = 8u * (1u >> ashift), t2 = 8u * (2u >> ashift), t3 = 8u * (3u >> ashift);
+      const uint32_t sub_cols = (uint32_t)p.a_tmem_cols / (uint32_t)CH;               // ATS: TMEM columns of one chunk
+      const uint64_t kSubIncB = ((uint64_t)p.b_stage_bytes / (uint64_t)CH) >> 4;      // one chunk's F tile inside a stage
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
+      [[maybe_unused]] long long prof_te = 0, prof_fa = 0, prof_fb = 0, prof_n = 0;
+      GH_BP_CLK(prof_t0);
       for (int u = u_begin; u < u_end; ++u, ++it) {
         const uint32_t ab = it & 1u, use = it >> 1;
+        GH_BP_CLK(prof_w0);
         mbar_wait_cl(bar_tempty + 8 * ab, (use & 1u) ^ 1u, 200u + ab);
+        GH_BP_ADD(prof_te, prof_w0);
         tc_fence_after_sync();
         const uint32_t acc = tmem_base + ab * 256u;
         for (int kc = 0; kc < p.nkc; ++kc) {
+          GH_BP_CLK(prof_w1);
           mbar_wait_cl(bar_fullA + 8 * sa, pa, 300u + sa);
+          GH_BP_ADD(prof_fa, prof_w1);
+          GH_BP_CLK(prof_w2);
           mbar_wait_cl(bar_fullB + 8 * sb, pb, 320u + sb);
+          GH_BP_ADD(prof_fb, prof_w2);
+#ifdef GH_BP_PROFILE
+          ++prof_n;
+#endif
           tc_fence_after_sync();
           const uint64_t da = dA0 + sa * kStageInc, db = dB0 + sb * kStageIncB;
+          if constexpr (ATS) {
+            // A from tensor memory: k-step ks of chunk sc reads the 8 columns of generated k-step ks / areuse
+            const uint32_t ta0 = tmem_base + (sa & 1u) * 256u + (uint32_t)p.NT + (sa >> 1) * (uint32_t)p.a_tmem_cols;
+#pragma unroll
+            for (int sc = 0; sc < CH; ++sc) {
+              const int ch = kc * CH + sc;                                     // chunk index within the unit
+              const uint32_t ta = ta0 + (uint32_t)sc * sub_cols;
+              const uint64_t dbs = db + (uint64_t)sc * kSubIncB;
+              if (ch < full_chunks) {
+                umma2_ts<KIND>(acc, ta, dbs, idesc, ch != 0 ? 1u : 0u);
+                umma2_ts<KIND>(acc, ta + t1, dbs + kBInc, idesc, 1u);
+                umma2_ts<KIND>(acc, ta + t2, dbs + 2 * kBInc, idesc, 1u);
+                umma2_ts<KIND>(acc, ta + t3, dbs + 3 * kBInc, idesc, 1u);
+              } else {
+                for (uint32_t ks = 0; ks < KC / T::kUmmaK; ++ks) {
+                  if ((int)(ch * KC + ks * T::kUmmaK) >= p.C) break;
+                  umma2_ts<KIND>(acc, ta + 8u * (ks >> ashift), dbs + ks * kBInc, idesc, (uint32_t)ch | ks);
+                }
+              }
+            }
+          } else
           // k-step ks reads the A data of k-step (ks & amask): with a pooling factor k >= 2 * UMMA_K the generated rows
           // repeat across k-steps, so only the first k-step of each run is generated (a1..a3 = 0/0/0, 1/2/2 or 1/2/3)
           if (kc < full_chunks) {
@@ -244,6 +333,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
           if (++sb == kBpBStages) { sb = 0; pb ^= 1u; }
         }
       }
+#ifdef GH_BP_PROFILE
+      {
+        long long prof_tot = 0;
+        GH_BP_ADD(prof_tot, prof_t0);
+        GH_BP_FLUSH(0, prof_tot);
+        GH_BP_FLUSH(1, prof_te);
+        GH_BP_FLUSH(2, prof_fa);
+        GH_BP_FLUSH(3, prof_fb);
+        GH_BP_FLUSH(4, prof_n);
+        GH_BP_FLUSH(12, 1);
+      }
+#endif
     }
     __syncwarp();
   } else if (warp < 6 || warp >= kBpEpi2Warp0) {
@@ -255,10 +356,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
     const int eidx = warp < 6 ? warp - 2 : 4 + (warp - kBpEpi2Warp0);
     const uint32_t my_store = store_smem + (uint32_t)eidx * (kBpStoreBufs * 4096u);
     uint32_t it = 0, buf = 0;
+    [[maybe_unused]] long long prof_tf = 0, prof_sb = 0;
+    GH_BP_CLK(prof_t0);
     for (int u = u_begin; u < u_end; ++u, ++it) {
       const GramBwdPairUnit w = gbp_decode(p, u);
       const uint32_t ab = it & 1u, use = it >> 1;
+      GH_BP_CLK(prof_w0);
       mbar_wait(bar_tfull + 8 * ab, use & 1u, 400u + ab);
+      GH_BP_ADD(prof_tf, prof_w0);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256u;
       const int crow0 = w.cb * 256 + (int)rank * 128 + q * 32;
@@ -268,8 +373,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
         if (x >= p.HW) break;                               // warp-uniform
         float v[32];
         tmem_ld32(taddr + (uint32_t)n0, v);
+        GH_BP_CLK(prof_w1);
         if (elected) tma_store_wait_read<kBpStoreBufs - 1>();     // the staging tile about to be reused has been read
         __syncwarp();
+        GH_BP_ADD(prof_sb, prof_w1);
         if (p.df_bf16) {
           // bf16 gradient: 64 B rows, SWIZZLE_64B (16 B chunk c of row r sits at chunk c ^ ((r >> 1) & 3))
           if constexpr (NHWC) {
@@ -321,6 +428,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_leader + 8 * ab);
     }
+#ifdef GH_BP_PROFILE
+    if (warp == 2 && rank == 0 && lane == 0) {
+      long long prof_tot = 0;
+      GH_BP_ADD(prof_tot, prof_t0);
+      GH_BP_FLUSH(5, prof_tot);
+      GH_BP_FLUSH(6, prof_tf);
+      GH_BP_FLUSH(7, prof_sb);
+    }
+#endif
     if (elected) tma_store_wait_all<0>();
     __syncwarp();
   } else {
@@ -334,7 +450,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
     constexpr int NE = kBpMaxG * kBpMaxG / kBpGenThreads;   // table entries per generator thread
     const int grp = (warp - 6) / (kBpGroupThreads / 32);
     const int gall = threadIdx.x - 6 * 32;                  // 0..511 among all generator threads
-    const int gt = gall - grp * kBpGroupThreads;            // 0..127 = A row
+    // thread = A row. SS: any assignment works (0..127 in thread order); ATS: a warp can only write the TMEM lanes of
+    // its quarter (warp & 3), so the row is that quarter's lane
+    const int gt = ATS ? ((warp & 3) * 32 + lane) : (gall - grp * kBpGroupThreads);
     const uint32_t row = (uint32_t)gt, sw = row & 7u;
     const uint32_t row_off = (row >> 3) * kAtomBytes + sw * kRowBytes;
     const int gg = p.g * p.g;
@@ -374,6 +492,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
       named_bar_sync(1, kBpGenThreads);
     }
     int n0 = 0;                                             // sequence number of the unit's first K chunk
+    [[maybe_unused]] long long prof_ea = 0;
+    GH_BP_CLK(prof_t0);
     for (int u = u_begin; u < u_end; ++u, n0 += p.nkc) {
       const GramBwdPairUnit w = gbp_decode(p, u);
       // the table changes only when the next unit belongs to another image
@@ -385,9 +505,40 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
       for (int kc = (grp - (n0 & 3) + 4) & 3; kc < p.nkc; kc += kBpGroups) {
         const uint32_t n = (uint32_t)(n0 + kc);
         const uint32_t stage = n % (uint32_t)kBpAStages, phase = (n / (uint32_t)kBpAStages) & 1u;
+        GH_BP_CLK(prof_w0);
         mbar_wait(bar_emptyA + 8 * stage, phase ^ 1u, 500u + stage);
+        GH_BP_ADD(prof_ea, prof_w0);
         const uint32_t a_row = a_ring + stage * kBpTileBytes + row_off;
         const int dbase = kc * (int)KC;
+        if constexpr (ATS) {
+          // The same pieces as below (one table value per 16 B = 4 columns), written to this row's TMEM lane: 8 columns
+          // per generated k-step, only the k-steps the MMAs read.
+          tc_fence_after_sync();                            // the MMAs that read this stage have completed (emptyA)
+          const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (stage & 1u) * 256u + (uint32_t)p.NT +
+                                 (stage >> 1) * (uint32_t)p.a_tmem_cols;
+          const int jstep = 2 * p.areuse;
+          uint32_t col = 0;
+#pragma unroll
+          for (int sc = 0; sc < CH; ++sc) {
+            const int dsub = (dbase * CH) + sc * (int)KC;   // first channel of chunk sc of this stage
+            const bool full_chunk = dsub + (int)KC <= p.C;
+            for (int j0 = 0; j0 < 8; j0 += jstep, col += 8u) {
+              uint32_t t[2];
+#pragma unroll
+              for (int jj = 0; jj < 2; ++jj) {
+                const int d0 = dsub + (j0 + jj) * EPC;
+                const float v = (full_chunk || d0 < p.C) ? srow[d0 >> p.kshift] : 0.f;
+                t[jj] = (KIND == KIND_TF32) ? f32_to_tf32_rna(v) : pack_bf16x2(v, v);
+              }
+              tmem_st8_pairs(t_row + col, t[0], t[1]);
+            }
+          }
+          tmem_st_wait();
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(fullA_leader + 8 * stage);
+          continue;
+        }
         if (MODE == GRAM_POOL) {
           // A k-step is two 16 B chunks of the row. Only the k-steps the MMAs read are written: all four when the
           // pooling factor equals UMMA_K, every second one / the first one when it is 2x / >= 4x UMMA_K (p.areuse).
@@ -432,6 +583,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
         cur ^= 1;
       }
     }
+#ifdef GH_BP_PROFILE
+    if (warp == 6 && rank == 0 && lane == 0) {
+      long long prof_tot = 0;
+      GH_BP_ADD(prof_tot, prof_t0);
+      GH_BP_FLUSH(8, prof_tot);
+      GH_BP_FLUSH(9, prof_ea);
+    }
+#endif
   }
 
   __syncwarp();

@@ -118,6 +118,11 @@ static int g_opt_fwd_pair = -1;
 static int g_opt_bwd_pair = -1;
 static int g_opt_bwd_nt = 0;        // 0 = plan the x-tile width; 64..256 (multiple of 16) forces it (experiments)
 static int g_opt_bwd_stages = 0;    // 0 = by shape; a * 16 + b forces the A / B ring depths of the pair backward
+static int g_opt_bwd_ats = 0;       // pooled pair backward with the generated gradient tile in TENSOR memory (A operand of
+                                    // the MMAs read from TMEM, gram_bwd_pair.cuh ATS): 0 = never, 1 = whenever the free
+                                    // TMEM columns beside the two accumulators hold the A ring, -1 = auto (C >= 512)
+static int g_opt_bwd_ch = 1;        // K chunks per ring stage of the tensor-memory form: 1, 2 (eight MMAs per iteration of the
+                                    // issuing thread, when a doubled A ring fits), 0 = auto
 static int g_opt_tma_f32_type = 1;  // tensor-map data type for fp32 features: 0 = FLOAT32, 1 = TFLOAT32
 
 template <int KIND, int KP, bool NHWC>
@@ -303,44 +308,61 @@ static int gram_bwd_common(const void* F, int f_dtype, long long img_stride, lon
       // cheap), the remaining tiles cut into F stages of the width the x tile needs.
       q.a_stages = 4; q.b_stages = kBpMaxStages;
       if (g_opt_bwd_stages) { q.a_stages = g_opt_bwd_stages >> 4; q.b_stages = g_opt_bwd_stages & 15; }
+      {   // k-steps of a chunk that share one generated piece of A: pooling factor / UMMA_K, capped at the 4 of a chunk
+        const int umma_k = is_bf16 ? 16 : 8, kfac = (mode == GRAM_POOL) ? (C / g) : 1;
+        q.areuse = kfac >= 4 * umma_k ? 4 : (kfac >= 2 * umma_k ? 2 : 1);
+      }
+      // A operand in tensor memory: the A ring (a multiple of the four generator groups) takes the TMEM columns the two
+      // NT-wide accumulators leave free in their 256-column halves; shared memory then holds F stages only.
+      bool ats = mode == GRAM_POOL && (g_opt_bwd_ats == 1 || (g_opt_bwd_ats == -1 && C >= 512));
+      q.a_tmem_cols = 32 / q.areuse;
+      int ch = 1;
+      if (ats && g_opt_bwd_ch != 1 && q.NT + 2 * 2 * q.a_tmem_cols <= 256) ch = 2;
+      q.a_tmem_cols *= ch;
+      if (ats) {
+        if (q.NT + 4 * q.a_tmem_cols <= 256) q.a_stages = 8;
+        else if (q.NT + 2 * q.a_tmem_cols <= 256) q.a_stages = 4;
+        else ats = false;
+      }
+      q.a_smem_tiles = ats ? 0 : q.a_stages;
       {   // one F stage: NHWC [NT/2 position rows][128 B]; NCHW: ceil(NT/2 / KC) x-blocks of [KC k-rows][128 B]
         const int half = q.NT / 2;
         long long sb = nhwc ? (long long)half * 128 : (long long)((half + kc_elems - 1) / kc_elems) * kc_elems * 128;
-        sb = (sb + 1023) / 1024 * 1024;
+        sb = (sb + 1023) / 1024 * 1024 * ch;
         q.b_stage_bytes = (int)sb;
-        const long long fit = ((long long)(kBpRingTiles - q.a_stages) * kBpTileBytes) / sb;
+        const long long fit = ((long long)(kBpRingTiles - q.a_smem_tiles) * kBpTileBytes) / sb;
         if (q.b_stages > fit) q.b_stages = (int)fit;
         if (q.b_stages > kBpMaxStages) q.b_stages = kBpMaxStages;
         if (q.b_stages < 2) return GH_ERR_UNSUPPORTED;
       }
       q.nCB = (C + 255) / 256;
-      q.nkc = (C + kc_elems - 1) / kc_elems;
-      {   // k-steps of a chunk that share one generated piece of A: pooling factor / UMMA_K, capped at the 4 of a chunk
-        const int umma_k = is_bf16 ? 16 : 8, kfac = (mode == GRAM_POOL) ? (C / g) : 1;
-        q.areuse = kfac >= 4 * umma_k ? 4 : (kfac >= 2 * umma_k ? 2 : 1);
-      }
+      q.nkc = (C + kc_elems * ch - 1) / (kc_elems * ch);
       const long long tot = (long long)B * q.nHT * q.nCB;
       if (tot <= 0x7fffffffLL) {
         q.total_units = (int)tot;
         int npairs = ctas_p / 2;
         if (tot < npairs) npairs = (int)tot;
         cudaError_t e3 = cudaErrorInvalidValue;
-#define GH_LAUNCH_BP(KIND, MODE, NHWC)                                                                                 \
+#define GH_LAUNCH_BP(KIND, MODE, NHWC, ATS, CH)                                                                        \
         {                                                                                                              \
-          e3 = cudaFuncSetAttribute(gram_bwd_pair_kernel<KIND, MODE, NHWC>,                                            \
+          e3 = cudaFuncSetAttribute(gram_bwd_pair_kernel<KIND, MODE, NHWC, ATS, CH>,                                   \
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBpSmemBytes);                   \
           if (e3 != cudaSuccess) return (int)e3;                                                                       \
-          gram_bwd_pair_kernel<KIND, MODE, NHWC><<<2 * npairs, kBpThreads, kBpSmemBytes, st>>>(q, tmF, tmD);           \
+          gram_bwd_pair_kernel<KIND, MODE, NHWC, ATS, CH><<<2 * npairs, kBpThreads, kBpSmemBytes, st>>>(q, tmF, tmD);  \
         }
-#define GH_LAUNCH_BP2(KIND, MODE)                                                                                      \
+#define GH_LAUNCH_BP2(KIND, MODE, ATS, CH)                                                                             \
         {                                                                                                              \
-          if (nhwc) GH_LAUNCH_BP(KIND, MODE, true) else GH_LAUNCH_BP(KIND, MODE, false)                                \
+          if (nhwc) GH_LAUNCH_BP(KIND, MODE, true, ATS, CH) else GH_LAUNCH_BP(KIND, MODE, false, ATS, CH)              \
         }
-        if (is_bf16) {
-          if (mode == GRAM_POOL) GH_LAUNCH_BP2(KIND_BF16, GRAM_POOL) else GH_LAUNCH_BP2(KIND_BF16, GRAM_DENSE)
-        } else {
-          if (mode == GRAM_POOL) GH_LAUNCH_BP2(KIND_TF32, GRAM_POOL) else GH_LAUNCH_BP2(KIND_TF32, GRAM_DENSE)
+#define GH_LAUNCH_BP3(KIND)                                                                                            \
+        {                                                                                                              \
+          if (mode != GRAM_POOL) GH_LAUNCH_BP2(KIND, GRAM_DENSE, false, 1)                                             \
+          else if (!ats) GH_LAUNCH_BP2(KIND, GRAM_POOL, false, 1)                                                      \
+          else if (ch == 2) GH_LAUNCH_BP2(KIND, GRAM_POOL, true, 2)                                                    \
+          else GH_LAUNCH_BP2(KIND, GRAM_POOL, true, 1)                                                                 \
         }
+        if (is_bf16) GH_LAUNCH_BP3(KIND_BF16) else GH_LAUNCH_BP3(KIND_TF32)
+#undef GH_LAUNCH_BP3
 #undef GH_LAUNCH_BP2
 #undef GH_LAUNCH_BP
         return (int)cudaGetLastError();
@@ -480,6 +502,17 @@ int gh_version(void) { return 100; }
 
 int gh_sm_count(void) { return sm_count_cached(); }
 
+#ifdef GH_BP_PROFILE
+// Profile builds only (not part of include/gramhead.h): copies the 16 role counters of gram_bwd_pair_kernel and clears them.
+int gh_bp_profile_read(unsigned long long* out) {
+  unsigned long long zero[16] = {0};
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpyFromSymbol(out, g_bp_prof, sizeof(zero));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_bp_prof, zero, sizeof(zero));
+  return (int)e;
+}
+#endif
+
 int gh_set_option(const char* name, int value) {
   if (!name) return GH_ERR_BAD_ARG;
   const std::string key(name);
@@ -507,6 +540,16 @@ int gh_set_option(const char* name, int value) {
     const int a = value >> 4, b = value & 15;
     if (value != 0 && (a < kBpGroups || b < 2 || a > kBpRingTiles - 2 || b > kBpMaxStages)) return GH_ERR_BAD_ARG;
     g_opt_bwd_stages = value;
+    return 0;
+  }
+  if (key == "gram_bwd_ats") {
+    if (value < -1 || value > 1) return GH_ERR_BAD_ARG;
+    g_opt_bwd_ats = value;
+    return 0;
+  }
+  if (key == "gram_bwd_ch") {
+    if (value < 0 || value > 2) return GH_ERR_BAD_ARG;
+    g_opt_bwd_ch = value;
     return 0;
   }
   if (key == "tma_f32_type") {

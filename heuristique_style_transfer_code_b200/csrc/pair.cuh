@@ -126,6 +126,39 @@ __device__ __forceinline__ void umma2(uint32_t tmem_d, uint64_t desc_a, uint64_t
         : "memory");
   }
 }
+// Same product with the A operand read from TENSOR MEMORY instead of shared memory: [128 lanes = this CTA's rows][K
+// columns of 32 bit: one tf32 or two bf16 elements each], at the same TMEM address in both CTAs of the pair. The MMA
+// then fetches only B from shared memory (gram_bwd_pair.cuh, ATS: the generated gradient tile never touches smem).
+template <int KIND>
+__device__ __forceinline__ void umma2_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+  if constexpr (KIND == KIND_BF16) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// Warp-collective: lane l writes 8 consecutive 32-bit columns of TMEM lane (lane quarter of taddr) + l: four times `a`,
+// then four times `b` (one k-step of a generated operand row whose 16 B pieces are constant).
+__device__ __forceinline__ void tmem_st8_pairs(uint32_t taddr, uint32_t a, uint32_t b) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %2, %2, %2, %2};" ::"r"(taddr), "r"(a), "r"(b)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // Arrives on the barrier at this offset in BOTH CTAs once every MMA issued so far by this thread has finished.
 __device__ __forceinline__ void umma_commit2(uint32_t bar) {
   const uint16_t mask = 3;

@@ -11,6 +11,9 @@ from heuristique_style_transfer_code_b200 import _lib
 from heuristique_style_transfer_code_b200.build import build_library
 
 
+DEFAULT_BWD_ATS = 0       # gramhead.cu: g_opt_bwd_ats (the option state lives in the loaded library, i.e. in the process)
+
+
 @pytest.fixture(scope="module")
 def library():
     build_library()
@@ -68,6 +71,26 @@ def test_argument_validation_without_gpu(library):
     assert library.gh_maxpool2d_nhwc(dummy, 0, dummy, 1, 8, 8, 64, 3, 2, 2, None) == _lib.GH_ERR_BAD_ARG                     # pad > k/2
     assert library.gh_stem_space_to_depth(None, 1, 1, 1, 1, 1, 8, 8, None, 0, None) == _lib.GH_ERR_BAD_ARG
     assert library.gh_stem_space_to_depth(dummy, 1, 1, 1, 1, 1, 7, 8, dummy, 0, None) == _lib.GH_ERR_UNSUPPORTED             # odd H
+
+
+def test_option_validation_and_environment_hook(monkeypatch, library):
+    """gh_set_option refuses values outside each knob's set; GRAMHEAD_OPTIONS applies knobs when the library is loaded and
+    fails loudly on anything it cannot apply (a silently ignored knob would make a measurement lie)."""
+    for value, want in ((-1, 0), (1, 0), (0, 0), (2, _lib.GH_ERR_BAD_ARG), (-2, _lib.GH_ERR_BAD_ARG)):
+        assert library.gh_set_option(b"gram_bwd_ats", value) == want
+    assert library.gh_set_option(b"gram_bwd_nt", 100) == _lib.GH_ERR_BAD_ARG         # not a multiple of 16
+    assert library.gh_set_option(b"gram_bwd_nt", 224) == 0 and library.gh_set_option(b"gram_bwd_nt", 0) == 0
+    monkeypatch.setattr(_lib, "_LIB", None)
+    monkeypatch.setenv("GRAMHEAD_OPTIONS", "gram_bwd_ats=1, gram_bwd_nt=0")
+    _lib.lib()
+    for bad in ("gram_bwd_ats", "gram_bwd_ats=x", "no_such_option=1", "gram_bwd_ats=7"):
+        monkeypatch.setattr(_lib, "_LIB", None)
+        monkeypatch.setenv("GRAMHEAD_OPTIONS", bad)
+        with pytest.raises(_lib.GramHeadError, match="GRAMHEAD_OPTIONS"):
+            _lib.lib()
+    monkeypatch.delenv("GRAMHEAD_OPTIONS")
+    monkeypatch.setattr(_lib, "_LIB", None)
+    assert _lib.lib().gh_set_option(b"gram_bwd_ats", DEFAULT_BWD_ATS) == 0           # back to the shipped default
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

@@ -231,6 +231,66 @@ def test_pooled_gram_backward(ops, B, C, HW, g, dtype, path):
         assert err <= 1e-3
 
 
+class bwd_operand_in_tmem:
+    """Context manager: pooled pair backward with the generated gradient tile in tensor memory (1), in shared memory (0),
+    or as shipped (-1: tensor memory for C >= 512) -- gh_set_option("gram_bwd_ats")."""
+
+    def __init__(self, value):
+        self.value = value
+
+    def __enter__(self):
+        from heuristique_style_transfer_code_b200 import _lib
+        assert _lib.lib().gh_set_option(b"gram_bwd_ats", self.value) == 0
+        return self
+
+    def __exit__(self, *exc):
+        from heuristique_style_transfer_code_b200 import _lib
+        _lib.lib().gh_set_option(b"gram_bwd_ats", BWD_ATS_DEFAULT)
+        return False
+
+
+BWD_ATS_DEFAULT = 0
+
+
+@pytest.mark.parametrize("B,C,H,W,g,dtype,cl", [
+    (2, 512, 28, 28, 32, "f32", True),      # layer2, NHWC: x tile 160, A stage = 16 TMEM columns (k-steps reused twice)
+    (2, 1024, 14, 14, 32, "f32", True),     # layer3: one x tile of 208 (not a multiple of 32), 8 columns per stage
+    (2, 256, 8, 16, 32, "f32", True),       # pooling factor = UMMA_K: every k-step generated, 32 columns per stage
+    (2, 256, 8, 16, 32, "bf16", True),      # pooling factor 8 < UMMA_K 16: a k-step holds two table values
+    (2, 512, 28, 28, 32, "bf16", True),     # bf16: four A stages only (2 x 32 columns beside each accumulator)
+    (2, 1024, 14, 14, 32, "bf16", True),
+    (3, 2048, 14, 14, 32, "f32", True),     # eight 256-channel blocks, pooling factor 64
+    (1, 2048, 7, 7, 32, "bf16", True),      # layer4: x tile 64
+    (2, 512, 28, 28, 32, "f32", False),     # NCHW: F is the MN-major operand
+    (2, 1024, 14, 14, 32, "f32", False),
+    (2, 512, 28, 28, 32, "bf16", False),
+    (2, 160, 10, 20, 20, "bf16", False),    # C not a multiple of the K chunk: partial last chunk, padded rows
+    (2, 144, 10, 20, 18, "f32", False),
+    (40, 512, 28, 28, 32, "f32", True),     # several units per CTA pair: ring wrap, gradient-table switches
+    (300, 512, 8, 8, 32, "f32", True),
+])
+def test_pooled_gram_backward_with_the_gradient_tile_in_tensor_memory(ops, B, C, H, W, g, dtype, cl):
+    """The A operand (dG + dG^T, generated from the g x g descriptor gradient) written to TMEM by tcgen05.st and read from
+    there by the MMAs, against the fp64 oracle and against the shared-memory form: same operand values, same K order, so
+    the two agree to rounding of the last bit at most."""
+    torch.manual_seed(0)
+    x = torch.relu(torch.randn(B, C, H, W, device="cuda"))
+    if dtype == "bf16":
+        x = x.bfloat16()
+    xin = x.contiguous(memory_format=torch.channels_last) if cl else x.reshape(B, C, H * W)
+    dd = torch.randn(B, 2, g * g, device="cuda")
+    with kernel_path("pair"):
+        with bwd_operand_in_tmem(1):
+            ts = ops.gram_pool_bwd(xin, g, dd, 1)
+        with bwd_operand_in_tmem(0):
+            ss = ops.gram_pool_bwd(xin, g, dd, 1)
+    torch.cuda.synchronize()
+    ref = O.gram_pool_backward(npf(x).reshape(B, C, H * W), g, npf(dd[:, 1]))
+    err = O.rel_err(npf(ts).reshape(ref.shape), ref)
+    assert err <= (1e-3 if dtype == "f32" else 6e-3)
+    assert float((ts.float() - ss.float()).norm() / ss.float().norm()) <= 1e-6
+
+
 @pytest.mark.parametrize("B,C,HW", [(1, 64, 3136), (2, 256, 196), (1, 512, 100)])
 @pytest.mark.parametrize("path", PATHS)
 def test_dense_gram_backward(ops, B, C, HW, path):
