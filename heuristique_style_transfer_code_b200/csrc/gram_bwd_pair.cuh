@@ -39,9 +39,12 @@ namespace gh {
 // of the C >= 512 stages come mostly from L2 and want the ring as deep as shared memory allows (bytes in flight =
 // bandwidth x latency). Measured and rejected (profiles/r2_gram_bwd_experiments.md): ONE ring with a single full / empty
 // barrier pair per slot (halves the MMA issuer's waits and commits per chunk, but leaves only 4-5 slots: 5-17 % slower).
-// a_stages >= kBpGroups: generator group i produces the chunks n = i (mod 4); its next chunk n + 4 reuses the stage of
-// chunk n + 4 - a_stages, which must be a chunk this group (or an earlier one) has already PUBLISHED -- otherwise its
-// wait on the stage's `empty` barrier could run two phases ahead of the barrier and pass on the aliased parity.
+// a_stages >= the number of stage lanes (4 generator groups / CH chunks per stage, CH = 1 in the shared-memory form):
+// a group produces the stages n = lane (mod lanes); its next stage n + lanes reuses the slot of stage n + lanes -
+// a_stages. Before it started stage n it waited for the MMAs of stage n - a_stages, so everything up to there has been
+// consumed; with a_stages >= lanes that covers stage n + lanes - 2 * a_stages, the slot's last-but-one occupant: the
+// waiter is at most ONE phase ahead of the slot's `empty` barrier. With fewer stages it could be two phases ahead and
+// pass on the aliased parity (seen as a deadlock, caught by the bounded waits, when a 3-stage ring was tried).
 constexpr int kBpRingTiles = 9;                             // A stages + F tiles, in 16 KB tiles
 constexpr int kBpMaxStages = 12;                            // per ring (sizes the barrier arrays)
 constexpr uint32_t kBpTileBytes = 16384;                    // A: [128 c][128 B]; B: <= 128 x-columns x (K chunk) x elem
@@ -82,6 +85,8 @@ struct GramBwdPairParams {
   int a_smem_tiles;         // 16 KB tiles the generated-A ring occupies in shared memory: a_stages, or 0 when the A
                             // operand lives in tensor memory (ATS kernels: the whole ring then belongs to F)
   int a_tmem_cols;          // ATS: TMEM columns of one A stage = CH * 32 / areuse (only the k-steps that differ are stored)
+  int d_stride;             // TMEM columns between the two accumulators: 256, or NT rounded up to 32 in the ATS kernels,
+  int a_tmem_base;          // whose A ring takes the columns from 2 * d_stride on: stage s at a_tmem_base + s * a_tmem_cols
 };
 
 // -DGH_BP_PROFILE: per-role cycle accounting (clock64 around every mbarrier wait of one thread per role, summed over
@@ -128,19 +133,24 @@ __device__ __forceinline__ uint32_t f32_to_tf32_rna(float x) {
 //               tile twice (generator stores + the tensor core's operand fetch, 4 KB per MMA and CTA whatever N is)
 //               on top of the F tiles (TMA write + operand fetch) and the gradient staging (write + TMA read) --
 //               872 KB per C = 512 unit against 5 120 cycles of MMAs, i.e. more than the ~90 B/clk the kernels of this
-//               library are seen to sustain; with A in TMEM it is 488 KB. Stage s of the A ring sits in the columns the
-//               two accumulators leave free: (s & 1) * 256 + NT + (s >> 1) * a_tmem_cols.
+//               library are seen to sustain; with A in TMEM it is 488 KB. The two accumulators sit d_stride = NT (rounded
+//               up to 32) columns apart and the A ring takes the columns behind them: stage s at a_tmem_base +
+//               s * a_tmem_cols. (Measured: the shared-memory traffic was NOT the limit -- same speed with one chunk per
+//               stage; what the TMEM operand buys is room for CH > 1, below.)
 // CH          : K chunks (128 B operand rows: 32 tf32 / 64 bf16 input channels) per ring stage. The single thread that
 //               issues the MMAs needs ~570 cycles per loop iteration (two mbarrier waits, descriptor arithmetic moved to
 //               uniform registers, 4 UTCHMMA, 2-3 UTCBAR -- measured with -DGH_BP_PROFILE: ~185 of them in waits that pass
 //               at once), while the four MMAs of a chunk execute in 320 (N = 160) to 448 cycles: with one chunk per
 //               stage the ISSUER paces the C >= 512 stages (tensor pipe 57 % active). CH = 2 (ATS only: a doubled A
-//               stage fits TMEM, not shared memory) issues eight MMAs per iteration.
+//               stage fits TMEM, not shared memory) issues eight MMAs per iteration, CH = 4 sixteen. The four generator
+//               groups then share a stage: group i writes chunk i % CH of the stages n = i / CH (mod 4 / CH); a_stages
+//               >= 4 / CH keeps every waiter at most one phase ahead of its barrier (see kBpRingTiles above).
+//               CH = 4 was measured too: its 40 KB F stages leave a 3-deep ring and it loses to CH = 2.
 template <int KIND, int MODE, bool NHWC, bool ATS = false, int CH = 1>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
     gram_bwd_pair_kernel(const GramBwdPairParams p, const __grid_constant__ CUtensorMap tmF,
                          const __grid_constant__ CUtensorMap tmD) {
-  static_assert(CH == 1 || (CH == 2 && ATS), "a doubled stage needs the A operand in tensor memory");
+  static_assert(CH == 1 || ((CH == 2 || CH == 4) && ATS), "a multi-chunk stage needs the A operand in tensor memory");
   using T = KindTraits<KIND>;
   constexpr uint32_t KC = T::kElemsPerRow;                  // input channels per K chunk
   constexpr uint32_t kAtomBytesB = KC * kRowBytes;          // one 128 B-wide x block of the B tile: 4 KB | 8 KB
@@ -174,7 +184,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
     tma_prefetch_desc(&tmF);
     tma_prefetch_desc(&tmD);
     for (uint32_t s = 0; s < kBpAStages; ++s) {
-      mbar_init(bar_fullA + 8 * s, 2 * (kBpGroupThreads / 32));   // the stage's generator warps of both CTAs
+      mbar_init(bar_fullA + 8 * s, 2 * CH * (kBpGroupThreads / 32));   // the stage's generator warps of both CTAs
       mbar_init(bar_emptyA + 8 * s, 1);                           // multicast tcgen05.commit
     }
     for (uint32_t s = 0; s < kBpBStages; ++s) {
@@ -279,7 +289,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
         mbar_wait_cl(bar_tempty + 8 * ab, (use & 1u) ^ 1u, 200u + ab);
         GH_BP_ADD(prof_te, prof_w0);
         tc_fence_after_sync();
-        const uint32_t acc = tmem_base + ab * 256u;
+        const uint32_t acc = tmem_base + ab * (uint32_t)p.d_stride;
         for (int kc = 0; kc < p.nkc; ++kc) {
           GH_BP_CLK(prof_w1);
           mbar_wait_cl(bar_fullA + 8 * sa, pa, 300u + sa);
@@ -294,7 +304,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
           const uint64_t da = dA0 + sa * kStageInc, db = dB0 + sb * kStageIncB;
           if constexpr (ATS) {
             // A from tensor memory: k-step ks of chunk sc reads the 8 columns of generated k-step ks / areuse
-            const uint32_t ta0 = tmem_base + (sa & 1u) * 256u + (uint32_t)p.NT + (sa >> 1) * (uint32_t)p.a_tmem_cols;
+            const uint32_t ta0 = tmem_base + (uint32_t)p.a_tmem_base + sa * (uint32_t)p.a_tmem_cols;
 #pragma unroll
             for (int sc = 0; sc < CH; ++sc) {
               const int ch = kc * CH + sc;                                     // chunk index within the unit
@@ -365,7 +375,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
       mbar_wait(bar_tfull + 8 * ab, use & 1u, 400u + ab);
       GH_BP_ADD(prof_tf, prof_w0);
       tc_fence_after_sync();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256u;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * (uint32_t)p.d_stride;
       const int crow0 = w.cb * 256 + (int)rank * 128 + q * 32;
 #pragma unroll 1
       for (int n0 = 32 * eset; n0 < p.NT; n0 += 64) {
@@ -441,7 +451,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
     __syncwarp();
   } else {
     // =========================== A-tile generators: this CTA's 128 rows of M ===========================
-    // Group grp fills A stage grp, i.e. the K chunks n = unit_index * nkc + kc with n % 4 == grp. Thread = A row.
+    // Group grp fills chunk grp % CH of the stages n = unit_index * nkc + kc with n % (4 / CH) == grp / CH. Thread = A row.
     // POOL: every 16 B chunk of the row is one value of the per-image table sym = dP + dP^T repeated (the pooling
     // factor k is >= the elements of a chunk): 8 shared loads, 8 conversions and 8 16 B stores per K chunk. The
     // table of the NEXT unit's image is fetched into registers (all 512 generator threads share the work) while the
@@ -449,6 +459,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
     constexpr int EPC = 16 / (int)T::kElemBytes;            // elements per 16 B chunk: 4 (tf32) / 8 (bf16)
     constexpr int NE = kBpMaxG * kBpMaxG / kBpGenThreads;   // table entries per generator thread
     const int grp = (warp - 6) / (kBpGroupThreads / 32);
+    constexpr int kLanes = kBpGroups / CH;                  // groups sharing a stage: CH; stage lanes: 4 / CH
+    const int glane = grp / CH, gsub = grp % CH;            // this group: chunk gsub of the stages n = glane (mod kLanes)
     const int gall = threadIdx.x - 6 * 32;                  // 0..511 among all generator threads
     // thread = A row. SS: any assignment works (0..127 in thread order); ATS: a warp can only write the TMEM lanes of
     // its quarter (warp & 3), so the row is that quarter's lane
@@ -502,7 +514,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
       const int c = w.cb * 256 + (int)rank * 128 + (int)row;
       const bool row_ok = c < p.C;
       const float* srow = table + cur * kBpTableFloats + (row_ok ? (c >> p.kshift) * p.g : gg);
-      for (int kc = (grp - (n0 & 3) + 4) & 3; kc < p.nkc; kc += kBpGroups) {
+      for (int kc = (glane - (n0 & (kLanes - 1)) + kLanes) & (kLanes - 1); kc < p.nkc; kc += kLanes) {
         const uint32_t n = (uint32_t)(n0 + kc);
         const uint32_t stage = n % (uint32_t)kBpAStages, phase = (n / (uint32_t)kBpAStages) & 1u;
         GH_BP_CLK(prof_w0);
@@ -514,25 +526,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBpThreads, 1)
           // The same pieces as below (one table value per 16 B = 4 columns), written to this row's TMEM lane: 8 columns
           // per generated k-step, only the k-steps the MMAs read.
           tc_fence_after_sync();                            // the MMAs that read this stage have completed (emptyA)
-          const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (stage & 1u) * 256u + (uint32_t)p.NT +
-                                 (stage >> 1) * (uint32_t)p.a_tmem_cols;
-          const int jstep = 2 * p.areuse;
-          uint32_t col = 0;
+          const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)p.a_tmem_base +
+                                 stage * (uint32_t)p.a_tmem_cols;
+          const int jstep = 2 * p.areuse, nd = 4 / p.areuse;         // generated k-steps of a chunk: 4, 2 or 1
+          const uint32_t col = (uint32_t)gsub * ((uint32_t)p.a_tmem_cols / (uint32_t)CH);
+          const int dsub = (dbase * CH) + gsub * (int)KC;   // first channel of this group's chunk of the stage
+          const bool full_chunk = dsub + (int)KC <= p.C;
+          uint32_t t[8];
 #pragma unroll
-          for (int sc = 0; sc < CH; ++sc) {
-            const int dsub = (dbase * CH) + sc * (int)KC;   // first channel of chunk sc of this stage
-            const bool full_chunk = dsub + (int)KC <= p.C;
-            for (int j0 = 0; j0 < 8; j0 += jstep, col += 8u) {
-              uint32_t t[2];
+          for (int i = 0; i < 4; ++i) {
 #pragma unroll
-              for (int jj = 0; jj < 2; ++jj) {
-                const int d0 = dsub + (j0 + jj) * EPC;
-                const float v = (full_chunk || d0 < p.C) ? srow[d0 >> p.kshift] : 0.f;
-                t[jj] = (KIND == KIND_TF32) ? f32_to_tf32_rna(v) : pack_bf16x2(v, v);
-              }
-              tmem_st8_pairs(t_row + col, t[0], t[1]);
+            for (int jj = 0; jj < 2; ++jj) {
+              const int d0 = dsub + (i * jstep + jj) * EPC;
+              const float v = (i < nd && (full_chunk || d0 < p.C)) ? srow[d0 >> p.kshift] : 0.f;
+              t[2 * i + jj] = (KIND == KIND_TF32) ? f32_to_tf32_rna(v) : pack_bf16x2(v, v);
             }
           }
+          if (nd == 4) tmem_st32_pairs(t_row + col, t);
+          else if (nd == 2) tmem_st16_pairs(t_row + col, t);
+          else tmem_st8_pairs(t_row + col, t[0], t[1]);
           tmem_st_wait();
           tc_fence_before_sync();
           __syncwarp();

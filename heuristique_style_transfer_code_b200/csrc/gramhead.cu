@@ -118,11 +118,11 @@ static int g_opt_fwd_pair = -1;
 static int g_opt_bwd_pair = -1;
 static int g_opt_bwd_nt = 0;        // 0 = plan the x-tile width; 64..256 (multiple of 16) forces it (experiments)
 static int g_opt_bwd_stages = 0;    // 0 = by shape; a * 16 + b forces the A / B ring depths of the pair backward
-static int g_opt_bwd_ats = 0;       // pooled pair backward with the generated gradient tile in TENSOR memory (A operand of
+static int g_opt_bwd_ats = -1;      // pooled pair backward with the generated gradient tile in TENSOR memory (A operand of
                                     // the MMAs read from TMEM, gram_bwd_pair.cuh ATS): 0 = never, 1 = whenever the free
                                     // TMEM columns beside the two accumulators hold the A ring, -1 = auto (C >= 512)
-static int g_opt_bwd_ch = 1;        // K chunks per ring stage of the tensor-memory form: 1, 2 (eight MMAs per iteration of the
-                                    // issuing thread, when a doubled A ring fits), 0 = auto
+static int g_opt_bwd_ch = 0;        // K chunks per ring stage of the tensor-memory form, at most: 1, 2 (8 MMAs per iteration
+                                    // of the issuing thread, when the widened A ring fits TMEM), 0 = auto (2)
 static int g_opt_tma_f32_type = 1;  // tensor-map data type for fp32 features: 0 = FLOAT32, 1 = TFLOAT32
 
 template <int KIND, int KP, bool NHWC>
@@ -315,20 +315,30 @@ static int gram_bwd_common(const void* F, int f_dtype, long long img_stride, lon
       // A operand in tensor memory: the A ring (a multiple of the four generator groups) takes the TMEM columns the two
       // NT-wide accumulators leave free in their 256-column halves; shared memory then holds F stages only.
       bool ats = mode == GRAM_POOL && (g_opt_bwd_ats == 1 || (g_opt_bwd_ats == -1 && C >= 512));
-      q.a_tmem_cols = 32 / q.areuse;
+      // one chunk's F tile: NHWC [NT/2 position rows][128 B]; NCHW: ceil(NT/2 / KC) x-blocks of [KC k-rows][128 B]
+      long long sb1 = nhwc ? (long long)(q.NT / 2) * 128 : (long long)((q.NT / 2 + kc_elems - 1) / kc_elems) * kc_elems * 128;
+      sb1 = (sb1 + 1023) / 1024 * 1024;
       int ch = 1;
-      if (ats && g_opt_bwd_ch != 1 && q.NT + 2 * 2 * q.a_tmem_cols <= 256) ch = 2;
-      q.a_tmem_cols *= ch;
+      q.a_tmem_cols = 0; q.d_stride = 256; q.a_tmem_base = 0;
       if (ats) {
-        if (q.NT + 4 * q.a_tmem_cols <= 256) q.a_stages = 8;
-        else if (q.NT + 2 * q.a_tmem_cols <= 256) q.a_stages = 4;
-        else ats = false;
+        // Most chunks per stage first (fewer iterations of the issuing thread per MMA). The accumulators take 2 * NT32
+        // columns (NT rounded up to 32), the A ring the rest: stages of c * 32 / areuse columns, at least as many as the
+        // 4 / c stage lanes of the generator groups and at least 2; the F ring keeps at least four stages.
+        const int scols = 32 / q.areuse, cmax = g_opt_bwd_ch ? g_opt_bwd_ch : 2, nt32 = (q.NT + 31) / 32 * 32;
+        bool found = false;
+        for (int c = 2; c >= 1 && !found; c >>= 1) {
+          if (c > cmax || ((long long)kBpRingTiles * kBpTileBytes) / (c * sb1) < 4) continue;
+          int a = (512 - 2 * nt32) / (c * scols);
+          if (a > 8) a = 8;
+          if (a < 4 / c || a < 2) continue;
+          ch = c; q.a_stages = a; found = true;
+        }
+        if (!found) ats = false;
+        else { q.a_tmem_cols = ch * scols; q.d_stride = nt32; q.a_tmem_base = 2 * nt32; }
       }
       q.a_smem_tiles = ats ? 0 : q.a_stages;
-      {   // one F stage: NHWC [NT/2 position rows][128 B]; NCHW: ceil(NT/2 / KC) x-blocks of [KC k-rows][128 B]
-        const int half = q.NT / 2;
-        long long sb = nhwc ? (long long)half * 128 : (long long)((half + kc_elems - 1) / kc_elems) * kc_elems * 128;
-        sb = (sb + 1023) / 1024 * 1024 * ch;
+      {
+        long long sb = sb1 * ch;
         q.b_stage_bytes = (int)sb;
         const long long fit = ((long long)(kBpRingTiles - q.a_smem_tiles) * kBpTileBytes) / sb;
         if (q.b_stages > fit) q.b_stages = (int)fit;

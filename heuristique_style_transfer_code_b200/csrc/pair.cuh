@@ -158,6 +158,21 @@ __device__ __forceinline__ void tmem_st8_pairs(uint32_t taddr, uint32_t a, uint3
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %2, %2, %2, %2};" ::"r"(taddr), "r"(a), "r"(b)
                : "memory");
 }
+// The same for two and four k-steps in one instruction (16 / 32 columns): a TMEM store costs the issuing warp a few
+// hundred cycles under MMA load whatever its width, so a stage's k-steps leave together.
+__device__ __forceinline__ void tmem_st16_pairs(uint32_t taddr, const uint32_t (&t)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %2, %2, %2, %2, %3, %3, %3, %3, %4, %4, %4, %4};" ::"r"(taddr),
+      "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32_pairs(uint32_t taddr, const uint32_t (&t)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %1, %1, %1, %2, %2, %2, %2, %3, %3, %3, %3, %4, %4, %4, %4, "
+      "%5, %5, %5, %5, %6, %6, %6, %6, %7, %7, %7, %7, %8, %8, %8, %8};" ::"r"(taddr),
+      "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // Arrives on the barrier at this offset in BOTH CTAs once every MMA issued so far by this thread has finished.
 __device__ __forceinline__ void umma_commit2(uint32_t bar) {

@@ -42,8 +42,10 @@ int gh_sm_count(void);
  *   "gram_bwd_nt"                      0 = plan the x-tile width of the pair backward; 64..256 (multiple of 16) forces it
  *   "gram_bwd_stages"                  0 = by shape; a*16 + b = A / F ring depths of the pair backward (a >= 4)
  *   "gram_bwd_ats"                     pooled pair backward with the generated gradient tile in tensor memory (the MMAs read
- *                                      their A operand from TMEM): 0 = never, 1 = whenever the TMEM columns beside the two
- *                                      accumulators hold the A ring, -1 = for C >= 512 only
+ *                                      their A operand from TMEM): 0 = never, 1 = whenever the TMEM columns behind the two
+ *                                      accumulators hold the A ring, -1 = for C >= 512 only (default)
+ *   "gram_bwd_ch"                      K chunks per ring stage of that form (MMAs per iteration of the issuing thread / 4):
+ *                                      0 = as many as fit, at most 2 (default), 1, 2
  *   "tma_f32_type"                     tensor-map type for fp32 features: 1 = TFLOAT32 (round to nearest, default), 0 = FLOAT32
  *   "attn_gemm"                        ld.global attention family: 1 = tcgen05 split-bf16 GEMMs (default), 0 = fp32 FMA kernels
  *   "tgemm_tn"                         tile width of the TMA-fed attention GEMMs: 0 = planned (default), 128, 256

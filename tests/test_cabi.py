@@ -11,7 +11,7 @@ from heuristique_style_transfer_code_b200 import _lib
 from heuristique_style_transfer_code_b200.build import build_library
 
 
-DEFAULT_BWD_ATS = 0       # gramhead.cu: g_opt_bwd_ats (the option state lives in the loaded library, i.e. in the process)
+DEFAULT_BWD_ATS = -1      # gramhead.cu: g_opt_bwd_ats (the option state lives in the loaded library, i.e. in the process)
 
 
 @pytest.fixture(scope="module")
