@@ -612,8 +612,10 @@ def run_ours(args):
             ops.PROFILE = []
             bms = timed_region(train_step, tsteps, device, D)
             brec, ops.PROFILE = ops.PROFILE, None
+            bk, _ = summarise_profile(brec, peaks)
             train["bf16_handoff"] = {"value": round(gb * tsteps / (bms / 1e3), 1), "unit": "images/s",
-                                     "ms_per_step": round(bms / tsteps, 2), "head": head_totals(brec, tsteps, peaks)}
+                                     "ms_per_step": round(bms / tsteps, 2), "head": head_totals(brec, tsteps, peaks),
+                                     "kernel_us": {k: v["avg_us"] for k, v in bk.items()}}
             tmodel.set_backbone_mode("channels_last")
         if world > 1:
             # The same step with the per-GPU batch held at the single-GPU size (weak scaling, global batch gb * world):
