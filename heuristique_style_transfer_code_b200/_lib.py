@@ -50,6 +50,7 @@ _SIGNATURES = {
     "gh_gemm_planes": (c_int, [_P, c_longlong, c_longlong, c_int, _P, c_longlong, c_longlong, c_int, _P, _P, _P,
                                 c_longlong, c_longlong, c_int, c_int, c_int, c_int, _P]),
     "gh_tgemm_plan": (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "gh_gram_bwd_plan": (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_int)]),
     "gh_attn_head_fwd2": (c_int, [_P] * 7 + [c_int] * 4 + [_P] * 6 + [_P]),
     "gh_attn_head_bwd2_workspace": (c_longlong, [c_int, c_int, c_int]),
     "gh_attn_head_bwd2": (c_int, [_P] * 10 + [c_int] * 4 + [_P] * 8 + [_P]),

@@ -248,6 +248,57 @@ static int gram_fwd_common(const void* F, int f_dtype, long long img_stride, lon
   return (int)e;
 }
 
+// Launch plan of the CTA-pair backward (gram_bwd_pair.cuh) from the shape alone: x-tile width, ring depths, and whether the
+// generated gradient tile lives in tensor memory (ATS) with how many K chunks per ring stage (CH). Fills the plan fields of
+// `q`; false when the shape leaves fewer than two F stages. Also behind gh_gram_bwd_plan (host logic, testable without a GPU).
+static bool plan_bwd_pair(int C, int HW, int g, int mode, bool is_bf16, bool nhwc, GramBwdPairParams& q, bool* ats_out,
+                          int* ch_out) {
+  const int kc_elems = is_bf16 ? 64 : 32;
+  gbp_plan_tiles(HW, &q.NT, &q.nHT);
+  if (g_opt_bwd_nt) { q.NT = g_opt_bwd_nt; q.nHT = (HW + q.NT - 1) / q.NT; }
+  // ring depths: see gram_bwd_pair.cuh. Shared-memory form: four A stages (the generator groups need that many; the
+  // generated chunks are cheap), the remaining tiles cut into F stages of the width the x tile needs.
+  q.a_stages = 4; q.b_stages = kBpMaxStages;
+  if (g_opt_bwd_stages) { q.a_stages = g_opt_bwd_stages >> 4; q.b_stages = g_opt_bwd_stages & 15; }
+  {   // k-steps of a chunk that share one generated piece of A: pooling factor / UMMA_K, capped at the 4 of a chunk
+    const int umma_k = is_bf16 ? 16 : 8, kfac = (mode == GRAM_POOL && g > 0) ? (C / g) : 1;
+    q.areuse = kfac >= 4 * umma_k ? 4 : (kfac >= 2 * umma_k ? 2 : 1);
+  }
+  bool ats = mode == GRAM_POOL && (g_opt_bwd_ats == 1 || (g_opt_bwd_ats == -1 && C >= 512));
+  // one chunk's F tile: NHWC [NT/2 position rows][128 B]; NCHW: ceil(NT/2 / KC) x-blocks of [KC k-rows][128 B]
+  long long sb1 = nhwc ? (long long)(q.NT / 2) * 128 : (long long)((q.NT / 2 + kc_elems - 1) / kc_elems) * kc_elems * 128;
+  sb1 = (sb1 + 1023) / 1024 * 1024;
+  int ch = 1;
+  q.a_tmem_cols = 0; q.d_stride = 256; q.a_tmem_base = 0;
+  if (ats) {
+    // Most chunks per stage first (fewer iterations of the issuing thread per MMA). The accumulators take 2 * NT32
+    // columns (NT rounded up to 32), the A ring the rest: stages of c * 32 / areuse columns, at least as many as the
+    // 4 / c stage lanes of the generator groups and at least 2; the F ring keeps at least four stages.
+    const int scols = 32 / q.areuse, cmax = g_opt_bwd_ch ? g_opt_bwd_ch : 2, nt32 = (q.NT + 31) / 32 * 32;
+    bool found = false;
+    for (int c = 2; c >= 1 && !found; c >>= 1) {
+      if (c > cmax || ((long long)kBpRingTiles * kBpTileBytes) / (c * sb1) < 4) continue;
+      int a = (512 - 2 * nt32) / (c * scols);
+      if (a > 8) a = 8;
+      if (a < 4 / c || a < 2) continue;
+      ch = c; q.a_stages = a; found = true;
+    }
+    if (!found) ats = false;
+    else { q.a_tmem_cols = ch * scols; q.d_stride = nt32; q.a_tmem_base = 2 * nt32; }
+  }
+  q.a_smem_tiles = ats ? 0 : q.a_stages;
+  const long long sb = sb1 * ch;
+  q.b_stage_bytes = (int)sb;
+  const long long fit = ((long long)(kBpRingTiles - q.a_smem_tiles) * kBpTileBytes) / sb;
+  if (q.b_stages > fit) q.b_stages = (int)fit;
+  if (q.b_stages > kBpMaxStages) q.b_stages = kBpMaxStages;
+  q.nCB = (C + 255) / 256;
+  q.nkc = (C + kc_elems * ch - 1) / (kc_elems * ch);
+  *ats_out = ats;
+  *ch_out = ch;
+  return q.b_stages >= 2;
+}
+
 static int gram_bwd_common(const void* F, int f_dtype, long long img_stride, long long row_stride, long long x_stride,
                            int B, int C, int HW, int mode, int g, const float* dP, long long dp_img_stride,
                            const float* dG, void* dF_any, int df_dtype, long long df_img_stride, long long df_row_stride,
@@ -286,10 +337,11 @@ static int gram_bwd_common(const void* F, int f_dtype, long long img_stride, lon
     CUtensorMap tmF, tmD;
     const int kc_elems = is_bf16 ? 64 : 32;
     GramBwdPairParams q;
-    gbp_plan_tiles(HW, &q.NT, &q.nHT);
-    if (g_opt_bwd_nt) { q.NT = g_opt_bwd_nt; q.nHT = (HW + q.NT - 1) / q.NT; }
+    bool ats = false;
+    int ch = 1;
+    const bool planned = plan_bwd_pair(C, HW, g, mode, is_bf16, nhwc, q, &ats, &ch);
     bool mapped = false;
-    if (want_pair) {
+    if (want_pair && planned) {
       if (nhwc)     // F: K-major tiles [NT/2 position rows][128 B of channels]; dF: [32 x][32 c] tiles
         mapped = make_tensor_map_nhwc_cxb(&tmF, F, is_bf16, img_stride, x_stride, B, C, HW, kc_elems, q.NT / 2,
                                           g_opt_tma_f32_type) &&
@@ -304,49 +356,6 @@ static int gram_bwd_common(const void* F, int f_dtype, long long img_stride, lon
       q.dP = dP; q.dp_img_stride = dp_img_stride; q.g = g; q.kshift = p.kshift; q.dG = dG;
       q.scale = p.scale;
       q.df_bf16 = df16 ? 1 : 0;
-      // ring depths: see gram_bwd_pair.cuh. Four A stages (the generator groups need that many; the generated chunks are
-      // cheap), the remaining tiles cut into F stages of the width the x tile needs.
-      q.a_stages = 4; q.b_stages = kBpMaxStages;
-      if (g_opt_bwd_stages) { q.a_stages = g_opt_bwd_stages >> 4; q.b_stages = g_opt_bwd_stages & 15; }
-      {   // k-steps of a chunk that share one generated piece of A: pooling factor / UMMA_K, capped at the 4 of a chunk
-        const int umma_k = is_bf16 ? 16 : 8, kfac = (mode == GRAM_POOL) ? (C / g) : 1;
-        q.areuse = kfac >= 4 * umma_k ? 4 : (kfac >= 2 * umma_k ? 2 : 1);
-      }
-      // A operand in tensor memory: the A ring (a multiple of the four generator groups) takes the TMEM columns the two
-      // NT-wide accumulators leave free in their 256-column halves; shared memory then holds F stages only.
-      bool ats = mode == GRAM_POOL && (g_opt_bwd_ats == 1 || (g_opt_bwd_ats == -1 && C >= 512));
-      // one chunk's F tile: NHWC [NT/2 position rows][128 B]; NCHW: ceil(NT/2 / KC) x-blocks of [KC k-rows][128 B]
-      long long sb1 = nhwc ? (long long)(q.NT / 2) * 128 : (long long)((q.NT / 2 + kc_elems - 1) / kc_elems) * kc_elems * 128;
-      sb1 = (sb1 + 1023) / 1024 * 1024;
-      int ch = 1;
-      q.a_tmem_cols = 0; q.d_stride = 256; q.a_tmem_base = 0;
-      if (ats) {
-        // Most chunks per stage first (fewer iterations of the issuing thread per MMA). The accumulators take 2 * NT32
-        // columns (NT rounded up to 32), the A ring the rest: stages of c * 32 / areuse columns, at least as many as the
-        // 4 / c stage lanes of the generator groups and at least 2; the F ring keeps at least four stages.
-        const int scols = 32 / q.areuse, cmax = g_opt_bwd_ch ? g_opt_bwd_ch : 2, nt32 = (q.NT + 31) / 32 * 32;
-        bool found = false;
-        for (int c = 2; c >= 1 && !found; c >>= 1) {
-          if (c > cmax || ((long long)kBpRingTiles * kBpTileBytes) / (c * sb1) < 4) continue;
-          int a = (512 - 2 * nt32) / (c * scols);
-          if (a > 8) a = 8;
-          if (a < 4 / c || a < 2) continue;
-          ch = c; q.a_stages = a; found = true;
-        }
-        if (!found) ats = false;
-        else { q.a_tmem_cols = ch * scols; q.d_stride = nt32; q.a_tmem_base = 2 * nt32; }
-      }
-      q.a_smem_tiles = ats ? 0 : q.a_stages;
-      {
-        long long sb = sb1 * ch;
-        q.b_stage_bytes = (int)sb;
-        const long long fit = ((long long)(kBpRingTiles - q.a_smem_tiles) * kBpTileBytes) / sb;
-        if (q.b_stages > fit) q.b_stages = (int)fit;
-        if (q.b_stages > kBpMaxStages) q.b_stages = kBpMaxStages;
-        if (q.b_stages < 2) return GH_ERR_UNSUPPORTED;
-      }
-      q.nCB = (C + 255) / 256;
-      q.nkc = (C + kc_elems * ch - 1) / (kc_elems * ch);
       const long long tot = (long long)B * q.nHT * q.nCB;
       if (tot <= 0x7fffffffLL) {
         q.total_units = (int)tot;
@@ -522,6 +531,19 @@ int gh_bp_profile_read(unsigned long long* out) {
   return (int)e;
 }
 #endif
+
+int gh_gram_bwd_plan(int C, int HW, int g, int f_dtype, int channels_last, int* out) {
+  if (!out || C <= 0 || HW <= 0 || g <= 0 || (f_dtype != GH_DTYPE_F32 && f_dtype != GH_DTYPE_BF16)) return GH_ERR_BAD_ARG;
+  if (C % g != 0 || g > kBpMaxG || C / g < 8 || ilog2_exact(C / g) < 0) return GH_ERR_UNSUPPORTED;
+  GramBwdPairParams q;
+  bool ats = false;
+  int ch = 1;
+  if (!plan_bwd_pair(C, HW, g, GRAM_POOL, f_dtype == GH_DTYPE_BF16, channels_last != 0, q, &ats, &ch)) return GH_ERR_UNSUPPORTED;
+  out[0] = q.NT; out[1] = q.nHT; out[2] = ats ? 1 : 0; out[3] = ch; out[4] = q.a_stages; out[5] = q.b_stages;
+  out[6] = q.a_tmem_base + q.a_stages * q.a_tmem_cols;   // TMEM columns in use (ATS), 0 otherwise
+  out[7] = q.b_stages * q.b_stage_bytes + q.a_smem_tiles * (int)kBpTileBytes;   // ring bytes in shared memory
+  return 0;
+}
 
 int gh_set_option(const char* name, int value) {
   if (!name) return GH_ERR_BAD_ARG;

@@ -242,6 +242,14 @@ int gh_gemm_planes(const void* A_planes, long long lda, long long a_plane_stride
  * (tile width 256 or 128, number of K partitions <= max_split, resulting work units). No GPU needed. */
 int gh_tgemm_plan(int M, int N, int K, int max_split, int npairs, int* tn, int* ksplit, int* units);
 
+/* Host-only: the launch plan of the CTA-pair pooled Gram backward (gh_gram_pool_bwd on TMA-describable features) for one
+ * stage shape, under the current gh_set_option state. out[0..7] = x-tile width NT, x tiles per image, 1 if the generated
+ * gradient tile lives in tensor memory (the MMAs' A operand is read from TMEM) else 0, K chunks per ring stage (1 or 2),
+ * A-ring stages, F-ring stages, TMEM columns in use (<= 512; 0 for the shared-memory form), ring bytes in shared memory
+ * (<= 147 456). GH_ERR_UNSUPPORTED for shapes the pair kernels do not take (C % g, pooling factor < 8 or not a power of
+ * two, g > 32). No GPU needed. */
+int gh_gram_bwd_plan(int C, int HW, int g, int f_dtype, int channels_last, int* out);
+
 /* Forward. w_in_planes: planes of in_proj_weight (2, 3E, E); w_out_planes: planes of out_proj.weight (2, E, E) (dense,
  * plane_stride = rows*E). b_in, b_out, W_c, b_c fp32 as in gh_attn_head_fwd. Outputs: emb (B, E), logits (B, nc); saved
  * for backward: x_planes (2, B*L, E) bf16, qkv (B*L, 3E) fp32, probs (B, L, L) fp32, obar_planes (2, B, E) bf16.

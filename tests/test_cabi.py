@@ -93,6 +93,57 @@ def test_option_validation_and_environment_hook(monkeypatch, library):
     assert _lib.lib().gh_set_option(b"gram_bwd_ats", DEFAULT_BWD_ATS) == 0           # back to the shipped default
 
 
+def test_gram_backward_planner_host_logic(library):
+    """gh_gram_bwd_plan (no GPU needed): x-tile width, ring depths and the tensor-memory form of the pooled Gram backward.
+    Invariants for every shape: TMEM columns <= 512, ring bytes <= 9 tiles of 16 KB, A stages >= the generator groups'
+    stage lanes (4 / chunks per stage), at least two F stages, tiles cover HW."""
+    import ctypes
+
+    def plan(C, HW, g=32, dtype=_lib.GH_DTYPE_F32, cl=1):
+        out = (ctypes.c_int * 8)()
+        assert library.gh_gram_bwd_plan(C, HW, g, dtype, cl, out) == 0
+        return dict(zip(("NT", "nHT", "ats", "ch", "a_stages", "b_stages", "tmem_cols", "ring_bytes"), out))
+
+    # the three ResNet stages at 224 x 224, fp32 channels_last (the default hand-off)
+    s1, s2, s3 = plan(256, 3136), plan(512, 784), plan(1024, 196)
+    assert (s1["NT"], s1["nHT"], s1["ats"], s1["ch"]) == (224, 14, 0, 1)        # HBM-bound stage: shared-memory form
+    assert (s2["NT"], s2["nHT"], s2["ats"], s2["ch"], s2["a_stages"]) == (160, 5, 1, 2, 6)
+    assert (s3["NT"], s3["nHT"], s3["ats"], s3["ch"], s3["a_stages"]) == (208, 1, 1, 2, 4)
+    # bf16 features: twice the TMEM columns per chunk (no k-step reuse at pooling factor 16)
+    b2 = plan(512, 784, dtype=_lib.GH_DTYPE_BF16)
+    assert (b2["ats"], b2["ch"], b2["a_stages"]) == (1, 2, 3)
+    for C in (64, 256, 512, 1024, 2048):
+        for HW in (49, 64, 100, 196, 784, 3136, 12544):
+            for dtype in (_lib.GH_DTYPE_F32, _lib.GH_DTYPE_BF16):
+                for cl in (0, 1):
+                    for g in (8, 32):
+                        if C // g < 8:
+                            continue
+                        p = plan(C, HW, g, dtype, cl)
+                        assert 64 <= p["NT"] <= 256 and p["NT"] % 16 == 0 and p["NT"] * p["nHT"] >= HW
+                        assert p["tmem_cols"] <= 512 and p["ring_bytes"] <= 9 * 16384 and p["b_stages"] >= 2
+                        assert p["ch"] in (1, 2) and p["a_stages"] >= max(2, 4 // p["ch"])
+                        assert p["ats"] == 1 or (p["ch"] == 1 and p["tmem_cols"] == 0)
+                        assert p["ats"] == 0 or C >= 512                               # default: tensor-memory form for C >= 512
+    try:      # the knobs reach the plan
+        assert library.gh_set_option(b"gram_bwd_ats", 0) == 0
+        assert plan(512, 784)["ats"] == 0
+        assert library.gh_set_option(b"gram_bwd_ats", 1) == 0 and library.gh_set_option(b"gram_bwd_ch", 1) == 0
+        p = plan(512, 784)
+        assert (p["ats"], p["ch"], p["a_stages"]) == (1, 1, 8)
+        assert plan(256, 128)["ats"] == 1                                              # small maps leave TMEM for the A ring
+        assert library.gh_set_option(b"gram_bwd_nt", 224) == 0
+        assert plan(512, 784)["nHT"] == 4
+    finally:
+        library.gh_set_option(b"gram_bwd_ats", DEFAULT_BWD_ATS)
+        library.gh_set_option(b"gram_bwd_ch", 0)
+        library.gh_set_option(b"gram_bwd_nt", 0)
+    out = (ctypes.c_int * 8)()
+    assert library.gh_gram_bwd_plan(100, 784, 32, 0, 1, out) == _lib.GH_ERR_UNSUPPORTED      # C % g
+    assert library.gh_gram_bwd_plan(128, 784, 32, 0, 1, out) == _lib.GH_ERR_UNSUPPORTED      # pooling factor 4
+    assert library.gh_gram_bwd_plan(512, 784, 32, 0, 1, None) == _lib.GH_ERR_BAD_ARG
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setenv("GRAMHEAD_LIB", str(tmp_path / "nope.so"))
     monkeypatch.setattr(_lib, "_LIB", None)

@@ -1,6 +1,6 @@
 """SASS opcode census of csrc/libgramhead.so, per kernel (runs where cuobjdump is: no GPU needed):
 
-    python tools/sass_census.py > profiles/r2_sass_census.txt
+    python tools/sass_census.py > profiles/r3_sass_census.txt
 
 Counts the mnemonics that identify the Blackwell paths (B200_PROFILING.md): UTC*MMA = tcgen05.mma, LDTM / STTM =
 tcgen05.ld / .st, UTMALDG / UTMASTG / UTMAREDG = TMA loads / stores / reduce-adds, UBLKCP = bulk copies, HMMA = legacy
