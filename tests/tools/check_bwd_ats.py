@@ -20,6 +20,8 @@ CASES = [  # B, C, H, W, g, dtype, channels_last
     (2, 1024, 10, 20, 32, "bf16", False), (2, 160, 10, 20, 20, "bf16", False), (2, 144, 10, 20, 18, "f32", False),
     (40, 512, 28, 28, 32, "f32", True), (300, 512, 8, 8, 32, "f32", True), (1, 2048, 7, 7, 32, "bf16", True),
     (2, 256, 8, 16, 32, "bf16", True),            # pooling factor 8 < UMMA_K = 16: a k-step holds two table values
+    (75, 512, 28, 28, 32, "f32", True),           # 750 units on 74 pairs: uneven unit counts per pair
+    (37, 1024, 14, 14, 32, "f32", True),          # 148 units: two per pair
 ]
 
 
