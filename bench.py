@@ -510,6 +510,21 @@ def run_ours(args):
     cp1.record()                                               # close to h2d_alone_ms on a box whose driver blocks in it
     torch.cuda.synchronize(device)
     h2d_alone_ms = cp0.elapsed_time(cp1) / 3
+    # Does this box overlap a host->device copy with kernels at all? The same 154 MB copy on a side stream, issued together
+    # with one forward on resident data, no dependency between them: ~max(forward, copy) on a box that overlaps them (then
+    # e2e ~ value), ~forward + copy on one that does not (seen on part of the pool: e2e 8.8-9.7 ms per step against 6.3-6.7 ms
+    # with the same code and an asynchronous copy call; tools/diag_copy_overlap.py is the longer version of this probe).
+    probe_stream = torch.cuda.Stream(device)
+    x_probe = torch.empty_like(x)
+    torch.cuda.synchronize(device)
+    t_probe = time.perf_counter()
+    for _ in range(5):
+        with torch.cuda.stream(probe_stream):
+            x_probe.copy_(x_host, non_blocking=True)
+        infer_step()
+    torch.cuda.synchronize(device)
+    overlap_probe_ms = (time.perf_counter() - t_probe) / 5 * 1e3
+    del x_probe
     e2e_ms = timed_region(lambda: e2e_loop(args.steps), 1, device, D)
     e2e_value = total * args.steps / (e2e_ms / 1e3)
     h2d = B * 3 * IMAGE * IMAGE * 4
@@ -690,6 +705,7 @@ def run_ours(args):
                        "parallelism": f"batch-sharded x{world}, all_gather of logits+embeddings" if world > 1 else "single GPU"},
             "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(e2e_ms / args.steps, 3), "h2d_alone_ms": round(h2d_alone_ms, 3), "h2d_call_host_ms": round(h2d_issue_ms, 3),
+                    "forward_with_concurrent_copy_ms": round(overlap_probe_ms, 3),
                     "h2d_alone_GBps": round(h2d / h2d_alone_ms / 1e6, 1)},
             "gpu_launches": launches,
             "roofline": roof,
