@@ -111,6 +111,17 @@ class ClockSampler:
                 "how": "NVML, 10 ms period, during the timed region"}
 
 
+def guarded(name, fn, *a, **kw):
+    """Side legs (everything beside the headline numbers) must not cost the run its JSON line: a failure is reported in
+    the leg's place and on stderr. Only for legs without collectives -- a rank that skips one would hang the others."""
+    try:
+        return fn(*a, **kw)
+    except Exception as exc:                                           # noqa: BLE001 - reported, not hidden
+        import traceback
+        traceback.print_exc()
+        return {"error": f"{name}: {type(exc).__name__}: {exc}"[:400]}
+
+
 def timed_region(fn, steps, device, dist_mod):
     """barrier + synchronize, CUDA events on the current stream around exactly `steps` calls, max over ranks (ms)."""
     dist_mod.barrier(device)
@@ -525,10 +536,49 @@ def run_ours(args):
     torch.cuda.synchronize(device)
     overlap_probe_ms = (time.perf_counter() - t_probe) / 5 * 1e3
     del x_probe
-    e2e_ms = timed_region(lambda: e2e_loop(args.steps), 1, device, D)
+    # three passes of the K-step loop, each timed on its own; the MEDIAN pass is the e2e number and all three are kept in the
+    # record (a pass is 0.13 s: one host hiccup moves it by several per cent, a box that does not overlap moves all three)
+    e2e_passes = sorted(timed_region(lambda: e2e_loop(args.steps), 1, device, D) for _ in range(3))
+    e2e_ms = e2e_passes[1]
     e2e_value = total * args.steps / (e2e_ms / 1e3)
     h2d = B * 3 * IMAGE * IMAGE * 4
     d2h = total * (GRAM_SIZE * GRAM_SIZE + NUM_CLASSES) * 4
+
+    # ---- the same loop fed uint8 pixels (opt-in loader path, functions.uint8_transform): a quarter of the upload, ToTensor's
+    # /255 and Normalize applied on the GPU by gh_normalize_u8, the model sees bit for bit the fp32 batch the host transforms
+    # would have produced. Reported beside `e2e` (which keeps the reference loader's fp32 batches), never as it.
+    def e2e_uint8_leg():
+        from heuristique_style_transfer_code_b200.functions import IMAGENET_MEAN, IMAGENET_STD, _normalize_host
+        u8_host = torch.randint(0, 256, (B, 3, IMAGE, IMAGE), dtype=torch.uint8,
+                                generator=torch.Generator().manual_seed(7 + rank)).pin_memory()
+        same = torch.equal(ops.normalize_u8(u8_host[:8].to(device), IMAGENET_MEAN, IMAGENET_STD).cpu(),
+                           _normalize_host(u8_host[:8], IMAGENET_MEAN, IMAGENET_STD))
+
+        def loop(n):
+            results = HostCollector()
+            with torch.no_grad():
+                for (xb,) in cuda_prefetch(((u8_host,) for _ in range(n)), device, reuse_buffers=True):
+                    emb, logits = model(xb)
+                    if world > 1:
+                        logits = D.gather_rows(logits, total, world)
+                        emb = D.gather_rows(emb, total, world)
+                    results.push(emb, logits)
+            assert len(results.finish()) == n
+
+        loop(3)
+        passes = sorted(timed_region(lambda: loop(args.steps), 1, device, D) for _ in range(3))
+        return {"value": round(total * args.steps / (passes[1] / 1e3), 1), "unit": "images/s",
+                "ms_per_step": round(passes[1] / args.steps, 3), "passes_ms_per_step": [round(p / args.steps, 3) for p in passes],
+                "h2d_bytes_per_step": B * 3 * IMAGE * IMAGE, "d2h_bytes_per_step": d2h,
+                "device_batch_bit_identical_to_host_transforms": bool(same),
+                "input": "uint8 pixels in pinned host memory; /255 and Normalize on the GPU (gh_normalize_u8) on the upload stream"}
+
+    e2e_u8 = None
+    if not args.skip_uint8:
+        if world > 1:
+            e2e_u8 = e2e_uint8_leg()                  # collective inside: every rank runs it, a failure is fatal for all
+        else:
+            e2e_u8 = guarded("e2e_uint8", e2e_uint8_leg)
 
     # ---- opt-in backbone hand-off: encoder under bf16 autocast, channels_last; same batch, device resident.
     # Reported beside the headline, never as it: it changes the numerics of the cuDNN backbone (not of the head).
@@ -573,7 +623,7 @@ def run_ours(args):
     # against the fp32 torch port of the reference forward on the same GPU and weights; reported beside the headline.
     patchgan = None
     if not args.skip_patchgan and rank == 0:
-        patchgan = patchgan_leg(device, peaks, max(3, args.steps // 4))
+        patchgan = guarded("patchgan_head", patchgan_leg, device, peaks, max(3, args.steps // 4))
 
     # ---- configs[2]: training step, global batch 512 over the ranks (strong scaling), AdamW ----
     train = None
@@ -676,7 +726,7 @@ def run_ours(args):
 
     ref_gpu = None
     if world == 1 and not args.skip_reference_gpu:
-        ref_gpu = reference_gpu_legs(device, max(3, args.steps // 4))
+        ref_gpu = guarded("reference_gpu", reference_gpu_legs, device, max(3, args.steps // 4))
 
     cpu_base, cpu_extra = None, None
     if world == 1 and not args.skip_cpu:
@@ -689,7 +739,7 @@ def run_ours(args):
                               f"{torch.__version__} CPU fp32 eval/no_grad, {cores} threads, "
                               + ("unmodified reference class loaded from baseline/_ref" if kind == "reference"
                                  else "oracle/torch_port.py")}
-        cpu_extra = cpu_extra_legs(cores)
+        cpu_extra = guarded("cpu_extra", cpu_extra_legs, cores)
 
     line = {"metric": "images/sec", "value": round(value, 1), "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
@@ -704,9 +754,11 @@ def run_ours(args):
                        "l2_policy": "inputs larger than L2 (154 MB images, 210/105/51 MB stage activations per step)",
                        "parallelism": f"batch-sharded x{world}, all_gather of logits+embeddings" if world > 1 else "single GPU"},
             "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": round(e2e_ms / args.steps, 3), "h2d_alone_ms": round(h2d_alone_ms, 3), "h2d_call_host_ms": round(h2d_issue_ms, 3),
+                    "ms_per_step": round(e2e_ms / args.steps, 3), "passes_ms_per_step": [round(p / args.steps, 3) for p in e2e_passes],
+                    "h2d_alone_ms": round(h2d_alone_ms, 3), "h2d_call_host_ms": round(h2d_issue_ms, 3),
                     "forward_with_concurrent_copy_ms": round(overlap_probe_ms, 3),
                     "h2d_alone_GBps": round(h2d / h2d_alone_ms / 1e6, 1)},
+            "e2e_uint8": e2e_u8,
             "gpu_launches": launches,
             "roofline": roof,
             "cpu_baseline": cpu_base,
@@ -737,9 +789,11 @@ def run_ours(args):
         line["head_fwd_bwd_frac_of_bf16_peak"] = th.get("frac_of_bf16_peak_burst")
         bh = (train.get("bf16_handoff") or {}).get("head") or {}
         line["head_fwd_bwd_frac_of_bf16_peak_bf16_handoff"] = bh.get("frac_of_bf16_peak_burst")
-    if ref_gpu is not None:
+    if ref_gpu is not None and "error" not in ref_gpu:
         line["reference_gpu_infer_img_s"] = ref_gpu["infer_batch256"]["images_per_s"]
         line["reference_gpu_train_img_s"] = ref_gpu["train_batch512"]["images_per_s"]
+    if e2e_u8 and "value" in e2e_u8:
+        line["e2e_uint8_img_s"] = e2e_u8["value"]
     line["e2e_img_s"] = round(e2e_value, 1)
     emit(json.dumps(line))
 
@@ -779,6 +833,7 @@ def main():
     ap.add_argument("--skip-handoff", action="store_true")
     ap.add_argument("--skip-patchgan", action="store_true")
     ap.add_argument("--skip-reference-gpu", action="store_true")
+    ap.add_argument("--skip-uint8", action="store_true", help="no e2e_uint8 leg (opt-in uint8 upload)")
     ap.add_argument("--no-graph-train", action="store_true", help="training leg: eager step only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -35,6 +35,7 @@ _SIGNATURES = {
     "gh_transpose_cast": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_longlong, _P]),
     "gh_preprocess_frame": (c_int, [_P, c_longlong, c_int, c_int, c_int, _P, _P, _P, c_int, _P, _P, _P, c_int, _P, _P, _P,
                                      c_int, c_int, _P]),
+    "gh_normalize_u8": (c_int, [_P, _P, c_longlong, c_int, c_longlong, _P, _P, _P]),
     "gh_gemm_f32": (c_int, [_P, c_longlong, c_longlong, _P, c_longlong, c_longlong, _P, _P, c_longlong, c_int, c_int,
                              c_int, _P]),
     "gh_maxpool2d_nhwc": (c_int, [_P, c_int, _P] + [c_int] * 7 + [_P]),

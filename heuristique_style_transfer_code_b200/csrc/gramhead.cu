@@ -742,6 +742,27 @@ int gh_preprocess_frame(const unsigned char* frame, long long pitch_bytes, int H
   return (int)cudaGetLastError();
 }
 
+int gh_normalize_u8(const unsigned char* src, float* dst, long long images, int channels, long long hw,
+                    const float* mean_host, const float* std_host, void* stream) {
+  if (!src || !dst || !mean_host || !std_host || images <= 0 || hw <= 0) return GH_ERR_BAD_ARG;
+  if (channels <= 0 || channels > 4) return GH_ERR_UNSUPPORTED;
+  NormalizeU8Params p{};
+  p.src = src; p.dst = dst; p.hw = hw; p.C = channels;
+  for (int c = 0; c < channels; ++c) {
+    if (!(std_host[c] != 0.f)) return GH_ERR_BAD_ARG;             // torchvision's Normalize raises on a zero std
+    p.mean[c] = mean_host[c]; p.std[c] = std_host[c];
+  }
+  const long long total = images * channels * hw;
+  const bool quads = hw % 4 == 0 && (uintptr_t)src % 4 == 0 && (uintptr_t)dst % 16 == 0;
+  p.units = quads ? total / 4 : total;
+  const long long want = (p.units + 255) / 256;
+  const long long cap = (long long)gh_sm_count() * 16;            // grid-stride: a few resident CTAs per SM
+  const int grid = (int)(want < cap ? want : cap);
+  if (quads) normalize_u8_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  else normalize_u8_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  return (int)cudaGetLastError();
+}
+
 int gh_gemm_f32(const float* A, long long a_sm, long long a_sk, const float* Bm, long long b_sk, long long b_sn,
                 const float* bias, float* D, long long ldd, int M, int N, int K, void* stream) {
   if (!A || !Bm || !D || M <= 0 || N <= 0 || K <= 0) return GH_ERR_BAD_ARG;

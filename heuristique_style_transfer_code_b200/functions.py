@@ -111,7 +111,38 @@ def _copy_stream(device):
     return _COPY_STREAMS[key]
 
 
-def cuda_prefetch(batches, device, reuse_buffers=False):
+IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+# What a uint8 image batch handed to cuda_prefetch (and so to the train / evaluation loops) is normalised with on the
+# device: the constants of the reference's loaders (test_RESNET50_Truncate_gram_attention.py:65,
+# train_best_RESNET50_Truncate_gram_attention.py:43). None leaves uint8 tensors as they are.
+UINT8_NORMALIZE = (IMAGENET_MEAN, IMAGENET_STD)
+
+
+def uint8_transform(resize=256, crop=224):
+    """Loader transform for the opt-in uint8 upload: the reference's Resize + CenterCrop (test_...:62-63) followed by
+    PILToTensor instead of ToTensor + Normalize (:64-65). The batches are then (B, 3, H, W) uint8 -- a quarter of the
+    host->device bytes -- and cuda_prefetch applies ToTensor's /255 and Normalize on the GPU (ops.normalize_u8), giving the
+    model bit for bit the fp32 batch the reference's transform would have produced on the host."""
+    from torchvision import transforms
+    steps = [transforms.Resize(resize)] if resize else []
+    if crop:
+        steps.append(transforms.CenterCrop(crop))
+    return transforms.Compose(steps + [transforms.PILToTensor()])
+
+
+def _is_uint8_images(t):
+    return torch.is_tensor(t) and t.dtype == torch.uint8 and t.dim() == 4 and 1 <= t.shape[1] <= 4
+
+
+def _normalize_host(t, mean, std):
+    """ToTensor's scaling + Normalize for a uint8 batch that stays on the host (CPU runs of the loops): the same op
+    sequence torchvision executes per image (to float32, div 255, sub mean, div std)."""
+    shape = (1, -1, 1, 1)
+    out = t.to(torch.float32).div_(255)
+    return out.sub_(torch.tensor(mean, dtype=torch.float32).view(shape)).div_(torch.tensor(std, dtype=torch.float32).view(shape))
+
+
+def cuda_prefetch(batches, device, reuse_buffers=False, normalize="default"):
     """Yields the batches of `batches` (tuples / lists of tensors, e.g. a DataLoader) already on `device`.
     On CUDA, batch i+1 is uploaded on a side stream while batch i is being processed, so the host->device copy
     (154 MB for 256 images at 224x224) leaves the critical path; use pin_memory=True loaders for the copy to be
@@ -119,11 +150,18 @@ def cuda_prefetch(batches, device, reuse_buffers=False):
 
     reuse_buffers=True uploads into two fixed sets of device buffers instead of allocating per batch (no allocator
     traffic, constant memory): a yielded batch is then only valid until the next one is requested -- what loops that
-    consume a batch and move on (this package's train / evaluation loops) need; leave it False when batches are kept."""
+    consume a batch and move on (this package's train / evaluation loops) need; leave it False when batches are kept.
+
+    normalize: (mean, std) applied on the device to every (B, C <= 4, H, W) uint8 tensor of a batch after its upload --
+    ToTensor's /255 and Normalize, bit-identical to the host transforms (ops.normalize_u8), for loaders built with
+    uint8_transform(); "default" takes functions.UINT8_NORMALIZE (the reference's ImageNet constants), None disables it."""
     device = torch.device(device)
+    if normalize == "default":
+        normalize = UINT8_NORMALIZE
     if device.type != 'cuda':
         for batch in batches:
-            yield tuple(t.to(device) if torch.is_tensor(t) else t for t in batch)
+            yield tuple((_normalize_host(t, *normalize) if normalize is not None and _is_uint8_images(t) else t.to(device))
+                        if torch.is_tensor(t) else t for t in batch)
         return
     copy_stream = _copy_stream(device)
     # Uploads of this generator start after everything already queued on the consumer's stream: buffers of an earlier
@@ -133,18 +171,23 @@ def cuda_prefetch(batches, device, reuse_buffers=False):
     consumed = [None, None]           # per slot: event on the consumer's stream after its last use of the slot
     count = 0
 
-    def place(slot, pos, t):
-        if not reuse_buffers:
-            return t.to(device, non_blocking=True)
+    def staged(slot, key, shape, dtype):
         bufs = slots[slot]
-        buf = bufs.get(pos)
-        if buf is None or buf.dtype != t.dtype or buf.shape[1:] != t.shape[1:] or buf.shape[0] < t.shape[0] or t.dim() == 0:
-            if t.dim() == 0:
-                return t.to(device, non_blocking=True)
-            buf = torch.empty(t.shape, dtype=t.dtype, device=device)
-            bufs[pos] = buf
-        view = buf[:t.shape[0]]
+        buf = bufs.get(key)
+        if buf is None or buf.dtype != dtype or buf.shape[1:] != shape[1:] or buf.shape[0] < shape[0]:
+            buf = torch.empty(shape, dtype=dtype, device=device)
+            bufs[key] = buf
+        return buf[:shape[0]]
+
+    def place(slot, pos, t):
+        pixels = normalize is not None and _is_uint8_images(t)
+        if not reuse_buffers or t.dim() == 0:
+            moved = t.to(device, non_blocking=True)
+            return ops.normalize_u8(moved, *normalize) if pixels else moved
+        view = staged(slot, pos, t.shape, t.dtype)
         view.copy_(t, non_blocking=True)
+        if pixels:                                 # the uint8 pixels stay in their own staging buffer of the slot
+            return ops.normalize_u8(view, *normalize, out=staged(slot, (pos, "fp32"), t.shape, torch.float32))
         return view
 
     def upload(batch):

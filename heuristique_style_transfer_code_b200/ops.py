@@ -5,7 +5,8 @@ libgramhead.so. All functions require CUDA tensors and raise otherwise: there is
 """
 from __future__ import annotations
 
-from typing import List, Sequence, Tuple
+import ctypes
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 
@@ -293,6 +294,35 @@ def stem_space_to_depth(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
                                                z.data_ptr(), _dtype_code(z), _stream_ptr(x))
     check(rc, "gh_stem_space_to_depth")
     return z
+
+
+def normalize_u8(x: torch.Tensor, mean, std, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(B, C, H, W) uint8 pixels on the device -> the fp32 batch transforms.ToTensor() + transforms.Normalize(mean, std)
+    produce on the host (reference test_RESNET50_Truncate_gram_attention.py:64-65), bit for bit (gh_normalize_u8).
+    `out`: optional dense fp32 buffer of at least B images to write into (its first B images are returned)."""
+    _require_cuda(x, "x")
+    if x.dim() != 4 or x.dtype != torch.uint8 or not 1 <= x.shape[1] <= 4:
+        raise GramHeadError("gramhead: normalize_u8 takes a (B, C <= 4, H, W) uint8 batch")
+    mean, std = [float(v) for v in mean], [float(v) for v in std]
+    b, c, h, w = x.shape
+    if len(mean) != c or len(std) != c:
+        raise GramHeadError(f"gramhead: normalize_u8: {c} channels need {c} means and stds")
+    x = x.contiguous()
+    if out is None:
+        out = torch.empty((b, c, h, w), device=x.device, dtype=torch.float32)
+    else:
+        if (out.dtype != torch.float32 or out.device != x.device or out.dim() != 4 or out.shape[0] < b
+                or out.shape[1:] != x.shape[1:] or not out.is_contiguous()):
+            raise GramHeadError("gramhead: normalize_u8: `out` must be a dense fp32 (>= B, C, H, W) tensor on x's device")
+        out = out[:b]
+    if b == 0:
+        return out
+    fl = ctypes.c_float * c
+    work = dict(bytes=x.numel() * 5, flops=0, kind="normalize_u8")
+    with torch.cuda.device(x.device), _Timed(f"normalize_u8[C={c},HW={h}x{w}]", 1, x.device, **work):
+        rc = _lib.lib().gh_normalize_u8(x.data_ptr(), out.data_ptr(), b, c, h * w, fl(*mean), fl(*std), _stream_ptr(x))
+    check(rc, "gh_normalize_u8")
+    return out
 
 
 def patch_gram(maps: Sequence[torch.Tensor], ln_input: bool = True):

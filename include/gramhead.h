@@ -138,6 +138,15 @@ int gh_preprocess_frame(const unsigned char* frame, long long pitch_bytes, int H
                         int vkmax, const float* mean3_host, const float* std3_host, float* out, int OH, int OW,
                         void* stream);
 
+/* Loader-side counterpart of gh_preprocess_frame: a dense (images, channels, H, W) uint8 batch -> the fp32 batch the
+ * reference's loader transforms produce on the host, transforms.ToTensor() + transforms.Normalize(mean, std)
+ * (test_RESNET50_Truncate_gram_attention.py:64-65, train_best_RESNET50_Truncate_gram_attention.py:42-43):
+ *   dst = (float(src) / 255 - mean[c]) / std[c]   in IEEE fp32, bit-identical to the host result,
+ * so that a loader can hand over uint8 pixels (a quarter of the PCIe bytes) and the model still sees the same tensor.
+ * mean_host / std_host: HOST pointers to `channels` floats (channels <= 4, std != 0); hw = H * W. */
+int gh_normalize_u8(const unsigned char* src, float* dst, long long images, int channels, long long hw,
+                    const float* mean_host, const float* std_host, void* stream);
+
 /* The GEMM the attention entry points are built from, exposed for testing and reuse:
  *   D[m*ldd + n] = sum_k A[m*a_sm + k*a_sk] * B[k*b_sk + n*b_sn] (+ bias[n]),   fp32 in, fp32 out.
  * Runs on tcgen05 with split-bf16 operands (hi*hi + hi*lo + lo*hi, fp32 accumulate: ~1e-5 relative) when each operand

@@ -259,6 +259,32 @@ def test_host_collector_and_buffer_reusing_prefetch_on_cpu():
     assert len(got) == 4 and all(torch.equal(g[0], b[0]) and g[2] == "meta" for g, b in zip(got, batches))
 
 
+def test_uint8_loader_path_matches_the_reference_transforms_on_cpu():
+    """Opt-in uint8 upload: uint8_transform() + the normalisation cuda_prefetch applies == the reference's
+    Resize / CenterCrop / ToTensor / Normalize (test_RESNET50_Truncate_gram_attention.py:61-66), bit for bit."""
+    import numpy as np
+    from PIL import Image
+    from torchvision import transforms
+    from heuristique_style_transfer_code_b200 import functions as F
+    rng = np.random.default_rng(5)
+    images = [Image.fromarray(rng.integers(0, 256, (300 + 20 * i, 280, 3), dtype=np.uint8)) for i in range(3)]
+    reference = transforms.Compose([transforms.Resize(256), transforms.CenterCrop(224), transforms.ToTensor(),
+                                    transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+    want = torch.stack([reference(im) for im in images])
+    pixels = torch.stack([F.uint8_transform(256, 224)(im) for im in images])
+    assert pixels.dtype == torch.uint8 and pixels.shape == (3, 3, 224, 224)
+    labels = torch.tensor([0, 1, 2])
+    (got, lab), = list(F.cuda_prefetch(iter([(pixels, labels)]), "cpu"))
+    assert got.dtype == torch.float32 and torch.equal(got, want) and torch.equal(lab, labels)
+    (raw, _), = list(F.cuda_prefetch(iter([(pixels, labels)]), "cpu", normalize=None))
+    assert raw.dtype == torch.uint8 and torch.equal(raw, pixels)                # opt-out leaves the pixels alone
+    (half, _), = list(F.cuda_prefetch(iter([(pixels, labels)]), "cpu", normalize=((0.5,) * 3, (0.25,) * 3)))
+    assert torch.equal(half, (pixels.float() / 255 - 0.5) / 0.25)
+    mask = torch.zeros(2, 8, 8, dtype=torch.uint8)                              # not an image batch: passed through
+    (m2,), = list(F.cuda_prefetch(iter([(mask,)]), "cpu"))
+    assert m2.dtype == torch.uint8
+
+
 def test_checkpoint_converters_produce_what_load_model_loads(tmp_path):
     """a torchvision ResNet50 state_dict and a three-section checkpoint match nothing in
     load_model (reference behaviour, preserved); their converted bare-encoder form fills every encoder tensor."""

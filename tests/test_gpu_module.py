@@ -377,6 +377,91 @@ def test_cuda_prefetch_delivers_every_batch_intact(reuse):
     assert [round(float(s), 4) for s in labels] == [float(i) for i in range(len(sizes))]
 
 
+@pytest.mark.parametrize("shape", [(5, 3, 224, 224), (2, 3, 7, 9), (3, 1, 8, 8), (1, 4, 6, 6), (2, 3, 64, 66)])
+def test_normalize_u8_is_bit_identical_to_the_host_transforms(shape):
+    """gh_normalize_u8 == ToTensor + Normalize of the reference's loaders (test_...:64-65), bit for bit; quad and
+    single-element kernels (H*W a multiple of four or not), every byte value, an `out` buffer larger than the batch."""
+    from heuristique_style_transfer_code_b200 import ops
+    from heuristique_style_transfer_code_b200.functions import _normalize_host
+    from heuristique_style_transfer_code_b200._lib import GramHeadError
+    c = shape[1]
+    mean, std = [0.485, 0.456, 0.406, 0.5][:c], [0.229, 0.224, 0.225, 0.25][:c]
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randint(0, 256, shape, dtype=torch.uint8, generator=g)
+    n = min(256, x.numel())
+    x.view(-1)[:n] = torch.arange(n, dtype=torch.int64).to(torch.uint8)
+    want = _normalize_host(x, mean, std)
+    before = ops.LAUNCHES
+    got = ops.normalize_u8(x.cuda(), mean, std)
+    assert ops.LAUNCHES == before + 1
+    assert got.dtype == torch.float32 and torch.equal(got.cpu(), want)
+    buf = torch.full((shape[0] + 2,) + shape[1:], -7.0, device="cuda")
+    view = ops.normalize_u8(x.cuda(), mean, std, out=buf)
+    assert view.data_ptr() == buf.data_ptr() and torch.equal(view.cpu(), want) and (buf[shape[0]:] == -7.0).all()
+    with pytest.raises(GramHeadError):
+        ops.normalize_u8(x.cuda(), mean[:-1] if c > 1 else mean + [0.1], std)
+    with pytest.raises(GramHeadError):
+        ops.normalize_u8(x.cuda().float(), mean, std)
+    with pytest.raises(GramHeadError):
+        ops.normalize_u8(x.cuda(), mean, [0.0] * c)
+
+
+@pytest.mark.parametrize("reuse", [False, True])
+def test_cuda_prefetch_normalises_uint8_batches_on_the_device(reuse):
+    """The opt-in uint8 upload: what the loops hand to the model equals the host-normalised fp32 batch bit for bit, also
+    with recycled staging buffers, a ragged last batch and a busy consumer stream."""
+    from heuristique_style_transfer_code_b200.functions import _normalize_host, cuda_prefetch, IMAGENET_MEAN, IMAGENET_STD
+    g = torch.Generator().manual_seed(11)
+    sizes = [16, 16, 16, 16, 5]
+    host = [(torch.randint(0, 256, (n, 3, 64, 64), dtype=torch.uint8, generator=g).pin_memory(),
+             torch.full((n,), i, dtype=torch.int64).pin_memory()) for i, n in enumerate(sizes)]
+    w = torch.randn(2048, 2048, device="cuda")
+    kept = []
+    for x, y in cuda_prefetch(iter(host), "cuda", reuse_buffers=reuse):
+        assert x.is_cuda and x.dtype == torch.float32 and y.dtype == torch.int64
+        for _ in range(10):
+            w = torch.tanh(w @ w * 1e-4)
+        kept.append((x.clone(), y.clone()))
+    torch.cuda.synchronize()
+    assert len(kept) == len(sizes)
+    for (x, y), (hx, hy) in zip(kept, host):
+        assert torch.equal(x.cpu(), _normalize_host(hx, IMAGENET_MEAN, IMAGENET_STD)) and torch.equal(y.cpu(), hy)
+    raw = [b[0] for b in cuda_prefetch(iter(host[:1]), "cuda", normalize=None)]
+    assert raw[0].dtype == torch.uint8 and torch.equal(raw[0].cpu(), host[0][0])
+
+
+def test_evaluation_loop_on_uint8_batches_equals_the_fp32_loop():
+    """evaluate_model_test over a loader that yields uint8 pixels returns exactly what it returns for the same images
+    normalised on the host (the reference's loader output): same embeddings, predictions and probabilities."""
+    from torch.utils.data import DataLoader, Dataset
+    from torchvision import models
+    from heuristique_style_transfer_code_b200 import TruncatedResNet50_for_test
+    from heuristique_style_transfer_code_b200 import functions as F
+
+    class Pixels(Dataset):
+        def __init__(self, normalised):
+            g = torch.Generator().manual_seed(12)
+            self.x = torch.randint(0, 256, (15, 3, 64, 64), dtype=torch.uint8, generator=g)
+            if normalised:
+                self.x = F._normalize_host(self.x, F.IMAGENET_MEAN, F.IMAGENET_STD)
+            self.y = torch.arange(15) % 4
+            self.samples = [(f"img_{i}.png", int(self.y[i])) for i in range(15)]
+
+        def __len__(self):
+            return 15
+
+        def __getitem__(self, i):
+            return self.x[i], self.y[i]
+
+    torch.manual_seed(4)
+    model = TruncatedResNet50_for_test(models.resnet50(weights=None), 7, 4, 32, device="cuda").eval()
+    a = F.evaluate_model_test(model, DataLoader(Pixels(False), batch_size=6, shuffle=False), "cuda")
+    b = F.evaluate_model_test(model, DataLoader(Pixels(True), batch_size=6, shuffle=False), "cuda")
+    assert a[0].shape == (15, 1024) and a[4] == b[4] and len(a[4]) == 15
+    for u, v in zip(a[:4], b[:4]):
+        assert np.array_equal(u, v)
+
+
 @pytest.mark.parametrize("shape,k,s,p", [((4, 64, 112, 112), 3, 2, 1), ((2, 64, 57, 33), 3, 2, 1), ((3, 16, 9, 9), 2, 2, 0),
                                          ((2, 8, 7, 12), 3, 1, 1)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
