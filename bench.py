@@ -10,7 +10,10 @@ the sm_100a head (3 pooled-Gram launches + attention/classifier). Multi-GPU: the
 (weak scaling); the only collective is the all-gather of logits and embeddings, inside the timed region.
 
   value      images/s with the batch resident in HBM (154 MB of fp32 images per rank: larger than the 126 MB L2)
-  e2e        same through the public call model(x_host): pinned host batch -> H2D -> forward -> logits+embeddings D2H
+  e2e        same through the public call model(x_host): pinned host batch -> H2D -> forward -> logits+embeddings D2H;
+             the median of three passes of the K-step loop (all three under `passes_ms_per_step`)
+  e2e_uint8  the same loop fed uint8 pixels (opt-in loader path: a quarter of the upload, ToTensor + Normalize on the GPU,
+             bit-identical batch); reported beside e2e, never as it
   roofline   the HEAD kernel (Gram / attention) that takes the most time inside the timed steps, measured
              live with CUDA events; backbone-side kernels of the library (max pool, stem staging) are listed under
              `breakdown.kernels` only
