@@ -111,6 +111,28 @@ def main():
     manual(3)
     print(f"hand-written double buffering, no result read-back: {wall(lambda: manual(10), reps=2) / 10:.2f} ms per step", flush=True)
 
+    # Pinned host allocations inside a timed loop: HostCollector's ring needs 4 x (1 MB + 4 KB) of them; cudaHostAlloc maps
+    # the pages for every GPU of the box and its cost differs widely between hosts.
+    def pinned(nbytes):
+        t = time.perf_counter()
+        buf = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        ms = (time.perf_counter() - t) * 1e3
+        del buf
+        return ms
+
+    print("fresh pinned allocations: " + ", ".join(f"{n >> 10} KB {pinned(n):.2f} ms" for n in (5 << 10, 3 << 20, 5 << 20, 9 << 20)),
+          flush=True)
+    e2e(6)
+    warm = wall(lambda: e2e(10), reps=1) / 10
+    if hasattr(torch._C, "_host_emptyCache"):
+        torch.cuda.synchronize()
+        torch._C._host_emptyCache()                 # every ring slot of the next loop is a fresh cudaHostAlloc
+        cold = wall(lambda: e2e(10), reps=1) / 10
+        print(f"end-to-end loop, ring slots warm: {warm:.2f} ms per step; all 8 pinned buffers allocated inside the loop: "
+              f"{cold:.2f} ms per step (10 steps)", flush=True)
+    else:
+        print(f"end-to-end loop, ring slots warm: {warm:.2f} ms per step", flush=True)
+
 
 if __name__ == "__main__":
     main()
