@@ -752,12 +752,14 @@ int gh_normalize_u8(const unsigned char* src, float* dst, long long images, int 
     if (!(std_host[c] != 0.f)) return GH_ERR_BAD_ARG;             // torchvision's Normalize raises on a zero std
     p.mean[c] = mean_host[c]; p.std[c] = std_host[c];
   }
-  const long long total = images * channels * hw;
+  const long long planes = images * channels;
+  // with hw % 4 == 0 every plane starts 4 B (uint8) / 16 B (fp32) aligned whenever the batch does
   const bool quads = hw % 4 == 0 && (uintptr_t)src % 4 == 0 && (uintptr_t)dst % 16 == 0;
-  p.units = quads ? total / 4 : total;
-  const long long want = (p.units + 255) / 256;
-  const long long cap = (long long)gh_sm_count() * 16;            // grid-stride: a few resident CTAs per SM
-  const int grid = (int)(want < cap ? want : cap);
+  const long long groups = quads ? hw / 4 : hw;
+  const long long chunks = (groups + 256 * kNormUnroll - 1) / (256 * kNormUnroll);
+  if (planes > 0x7fffffffLL || chunks > 65535 || groups > 0x7fffffffLL) return GH_ERR_UNSUPPORTED;
+  p.groups = (int)groups;
+  const dim3 grid((unsigned)planes, (unsigned)chunks);
   if (quads) normalize_u8_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
   else normalize_u8_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
   return (int)cudaGetLastError();

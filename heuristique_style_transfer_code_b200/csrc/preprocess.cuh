@@ -77,38 +77,65 @@ __global__ void __launch_bounds__(256) preprocess_frame_kernel(const PreprocPara
 // ---- loader-side counterpart: a uint8 image batch normalised on the device -------------------------------------------------
 // The reference's loaders end in ToTensor + Normalize on the host (test_RESNET50_Truncate_gram_attention.py:64-65,
 // train_best_RESNET50_Truncate_gram_attention.py:42-43) and every batch crosses PCIe as fp32: 154 MB for 256 images at
-// 224 x 224, 2.8 ms at the 55 GB/s the host link gives -- hidden behind the forward on a box whose copy engine runs beside
-// kernels, added to it on one where it does not. Uploading the uint8 pixels (38.5 MB) and applying the two transforms
+// 224 x 224, 2.8 ms at the 55 GB/s the host link gives one GPU -- hidden behind the forward then, but the bound of the step
+// when eight ranks share the host (25 GB/s each). Uploading the uint8 pixels (38.5 MB) and applying the two transforms
 // here moves a quarter of the bytes; the arithmetic is the host's: float(b) / 255 (ToTensor), (v - mean[c]) / std[c]
 // (Normalize), IEEE fp32 with correctly rounded divisions, so the fp32 batch is bit-identical to the loader's.
-// One thread = four pixels of one plane (one 4 B load, one 16 B store: both fully coalesced per warp), grid-stride.
+// A byte has 256 values and a plane one (mean, std): each CTA works inside ONE plane (grid x = plane, grid y = chunk of it,
+// so no 64-bit division per element), builds the plane's 256-entry table of results once -- thread t computes
+// ((float)t / 255 - mean) / std with the two correctly rounded divisions -- and the pixels become shared-memory lookups:
+// the arithmetic per value is the host's, done once per byte value instead of once per pixel (the first version, which
+// divided per pixel behind a 64-bit channel computation, reached 0.35 of the HBM roofline:
+// profiles/r4b_normalize_u8_timing_first_version.log). One thread = kNormUnroll groups of VEC pixels, 256 threads apart:
+// all loads of a thread are issued before the first use; with VEC = 4 a warp loads 128 B and stores 512 B contiguous per
+// instruction.
 struct NormalizeU8Params {
   const uint8_t* src;       // (N, C, H, W) uint8, dense
   float* dst;               // (N, C, H, W) fp32, dense
   long long hw;             // H * W
-  long long units;          // quads (hw % 4 == 0) or single elements
+  int groups;               // per plane: hw / VEC
   int C;
   float mean[4], std[4];
 };
 
+constexpr int kNormUnroll = 8;
+
 template <int VEC>
 __global__ void __launch_bounds__(256) normalize_u8_kernel(const NormalizeU8Params p) {
-  const long long step = (long long)gridDim.x * blockDim.x;
-  for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < p.units; u += step) {
-    const long long e = u * VEC;
-    const int c = (int)((e / p.hw) % p.C);
-    const float m = c == 0 ? p.mean[0] : c == 1 ? p.mean[1] : c == 2 ? p.mean[2] : p.mean[3];   // selects, not a
-    const float s = c == 0 ? p.std[0] : c == 1 ? p.std[1] : c == 2 ? p.std[2] : p.std[3];       // local-memory copy
-    if (VEC == 4) {
-      const unsigned raw = __ldg(reinterpret_cast<const unsigned*>(p.src + e));
-      float4 o;
-      o.x = __fdiv_rn(__fdiv_rn((float)(raw & 0xffu), 255.0f) - m, s);
-      o.y = __fdiv_rn(__fdiv_rn((float)((raw >> 8) & 0xffu), 255.0f) - m, s);
-      o.z = __fdiv_rn(__fdiv_rn((float)((raw >> 16) & 0xffu), 255.0f) - m, s);
-      o.w = __fdiv_rn(__fdiv_rn((float)(raw >> 24), 255.0f) - m, s);
-      __stcs(reinterpret_cast<float4*>(p.dst + e), o);
-    } else {
-      p.dst[e] = __fdiv_rn(__fdiv_rn((float)__ldg(p.src + e), 255.0f) - m, s);
+  __shared__ float table[256];
+  const long long plane = blockIdx.x;
+  const int c = (int)(blockIdx.x % (unsigned)p.C);
+  const float m = c == 0 ? p.mean[0] : c == 1 ? p.mean[1] : c == 2 ? p.mean[2] : p.mean[3];
+  const float s = c == 0 ? p.std[0] : c == 1 ? p.std[1] : c == 2 ? p.std[2] : p.std[3];
+  table[threadIdx.x] = __fdiv_rn(__fdiv_rn((float)threadIdx.x, 255.0f) - m, s);     // ToTensor, Normalize
+  __syncthreads();
+  const uint8_t* __restrict__ src = p.src + plane * p.hw;
+  float* __restrict__ dst = p.dst + plane * p.hw;
+  const int first = blockIdx.y * (256 * kNormUnroll) + threadIdx.x;
+  if (VEC == 4) {
+    unsigned raw[kNormUnroll];
+#pragma unroll
+    for (int j = 0; j < kNormUnroll; ++j) {
+      const int g = first + j * 256;
+      raw[j] = g < p.groups ? __ldg(reinterpret_cast<const unsigned*>(src) + g) : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < kNormUnroll; ++j) {
+      const int g = first + j * 256;
+      if (g < p.groups) {
+        float4 o;
+        o.x = table[raw[j] & 0xffu];
+        o.y = table[(raw[j] >> 8) & 0xffu];
+        o.z = table[(raw[j] >> 16) & 0xffu];
+        o.w = table[raw[j] >> 24];
+        __stcs(reinterpret_cast<float4*>(dst) + g, o);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < kNormUnroll; ++j) {
+      const int g = first + j * 256;
+      if (g < p.groups) dst[g] = table[__ldg(src + g)];
     }
   }
 }
