@@ -528,8 +528,9 @@ def run_ours(args):
     h2d_alone_ms = cp0.elapsed_time(cp1) / 3
     # Does this box overlap a host->device copy with kernels at all? The same 154 MB copy on a side stream, issued together
     # with one forward on resident data, no dependency between them: ~max(forward, copy) on a box that overlaps them (then
-    # e2e ~ value), ~forward + copy on one that does not (seen on part of the pool: e2e 8.8-9.7 ms per step against 6.3-6.7 ms
-    # with the same code and an asynchronous copy call; tools/diag_copy_overlap.py is the longer version of this probe).
+    # e2e ~ value), ~forward + copy on one that does not. (Earlier runs read e2e 8.8-9.7 ms per step on part of the pool;
+    # DESIGN section 5 traces that to a pinned allocation inside the timed pass, not to missing overlap.
+    # tools/diag_copy_overlap.py is the longer version of this probe.)
     probe_stream = torch.cuda.Stream(device)
     x_probe = torch.empty_like(x)
     torch.cuda.synchronize(device)
