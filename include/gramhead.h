@@ -83,10 +83,13 @@ int gh_gram_dense_fwd(const void* F, int f_dtype, long long img_stride, long lon
 /* torch.nn.functional.adaptive_avg_pool2d(G, (g, g)) on (B, C, C) with torch's bin rule
  * [floor(i*C/g), ceil((i+1)*C/g)), written to desc[:, l, :] of a (B, L, g*g) buffer.  (:51-55) */
 int gh_adaptive_pool_fwd(const float* G, int B, int C, int g, float* desc, int l, int L, void* stream);
-/* Its backward: dG (B, C, C) from d_desc[:, l, :]. */
+/* Its backward (AdaptiveAvgPool2DBackward of Models/Models_RESNET50_TRUNCATE_GRAM_with_Attention.py:51-52, reached from
+ * loss.backward(), functions/functions_RESNET50_Truncate_Gram_Attention.py:135): dG (B, C, C) from d_desc[:, l, :]. */
 int gh_adaptive_pool_bwd(const float* d_desc, int l, int L, int B, int C, int g, float* dG, void* stream);
 
-/* Pooled Gram, backward (autograd of the three reference lines above):
+/* Pooled Gram, backward: what loss.backward() (functions/functions_RESNET50_Truncate_Gram_Attention.py:135) runs for
+ * Models/Models_RESNET50_TRUNCATE_GRAM_with_Attention.py:26-30, :51-52, :54-55 (BmmBackward, DivBackward,
+ * AdaptiveAvgPool2DBackward, StackBackward):
  *   dF[b] = (dG + dG^T) F[b] / HW,  dG[c][d] = d_desc[b, l, (c/k)*g + d/k] / k^2.
  * dF: dtype df_dtype, element (b,c,x) at dF[b*df_img_stride + c*df_row_stride + x*df_x_stride]; overwritten. F and dF
  * must use the same layout (both x contiguous or both c contiguous, see gh_gram_pool_fwd). df_dtype = GH_DTYPE_BF16
@@ -97,7 +100,9 @@ int gh_gram_pool_bwd(const void* F, int f_dtype, long long img_stride, long long
                      int C, int HW, int g, const float* d_desc, int l, int L, void* dF, int df_dtype,
                      long long df_img_stride, long long df_row_stride, long long df_x_stride, int max_ctas, void* stream);
 
-/* Dense Gram, backward: dF[b] = (dG[b] + dG[b]^T) F[b] / HW with dG (B, C, C) fp32. Requires C % 16 == 0. */
+/* Dense Gram, backward (autograd of gram_matrix(), Models/...Attention.py:26-30, as style transfer drives it:
+ * functions/functions_RESNET50_Truncate_Gram_Attention.py:293): dF[b] = (dG[b] + dG[b]^T) F[b] / HW with dG (B, C, C) fp32.
+ * Requires C % 16 == 0. */
 int gh_gram_dense_bwd(const void* F, int f_dtype, long long img_stride, long long row_stride, long long x_stride, int B,
                       int C, int HW, const float* dG, void* dF, int df_dtype, long long df_img_stride,
                       long long df_row_stride, long long df_x_stride, int max_ctas, void* stream);
@@ -238,7 +243,8 @@ int gh_gram_mse(const float* G, const float* G_target, long long n, float* dG, f
  * gh_attn_head_fwd2 for the descriptors. n % 4 == 0, src 16 B aligned. */
 int gh_split_bf16(const float* src, void* planes, long long n, long long plane_stride, void* stream);
 
-/* The GEMM gh_attn_head_fwd2 / _bwd2 are built from, exposed for testing and reuse:
+/* The GEMM gh_attn_head_fwd2 / _bwd2 are built from (the F.linear / matmul calls torch's multi_head_attention_forward makes
+ * for self.attention, Models/...Attention.py:58, and their autograd), exposed for testing and reuse:
  *   D[m*ldd + n] (fp32)  or  D_planes (hi/lo bf16, d_plane_stride apart)  =  sum_k A(m,k) B(n,k) (+ bias[n])
  * with split-plane operands. a_mn = 0: A(m,k) at m*lda + k; a_mn = 1: A(m,k) at k*lda + m (M % 64 == 0). Same for B
  * with ldb / N. Exactly one of D, D_planes is non-NULL. K is split in at most max_split partitions (1 for D_planes).
@@ -259,7 +265,7 @@ int gh_tgemm_plan(int M, int N, int K, int max_split, int npairs, int* tn, int* 
  * two, g > 32). No GPU needed. */
 int gh_gram_bwd_plan(int C, int HW, int g, int f_dtype, int channels_last, int* out);
 
-/* Forward. w_in_planes: planes of in_proj_weight (2, 3E, E); w_out_planes: planes of out_proj.weight (2, E, E) (dense,
+/* Forward (Models/Models_RESNET50_TRUNCATE_GRAM_with_Attention.py:56-61 / :108-114). w_in_planes: planes of in_proj_weight (2, 3E, E); w_out_planes: planes of out_proj.weight (2, E, E) (dense,
  * plane_stride = rows*E). b_in, b_out, W_c, b_c fp32 as in gh_attn_head_fwd. Outputs: emb (B, E), logits (B, nc); saved
  * for backward: x_planes (2, B*L, E) bf16, qkv (B*L, 3E) fp32, probs (B, L, L) fp32, obar_planes (2, B, E) bf16.
  * Five launches: split X, in_proj GEMM, per-image scores/softmax/value mix, out_proj GEMM, classifier. Results are
@@ -271,7 +277,8 @@ int gh_attn_head_fwd2(const float* desc, const void* w_in_planes, const float* b
 /* Bytes of `workspace` gh_attn_head_bwd2 needs (16 B aligned). */
 long long gh_attn_head_bwd2_workspace(int B, int L, int E);
 
-/* Backward of gh_attn_head_fwd2. Outputs as in gh_attn_head_bwd (each may be NULL; overwritten, not accumulated).
+/* Backward of gh_attn_head_fwd2 (autograd of Models/...Attention.py:56-61, driven by loss.backward(),
+ * functions/functions_RESNET50_Truncate_Gram_Attention.py:135). Outputs as in gh_attn_head_bwd (each may be NULL; overwritten, not accumulated).
  * Four launches: gradient prep (demb planes, db_out, dW_c, db_c), {dObar, dW_out} GEMMs, per-image softmax/score
  * backward (dQKV planes, db_in), {dW_in, d_desc} GEMMs. K partitions of a GEMM meet in fp32 reduce-adds whose order is
  * not fixed: gradients are reproducible to fp32 rounding, not bitwise. */
