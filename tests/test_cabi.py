@@ -71,6 +71,13 @@ def test_argument_validation_without_gpu(library):
     assert library.gh_maxpool2d_nhwc(dummy, 0, dummy, 1, 8, 8, 64, 3, 2, 2, None) == _lib.GH_ERR_BAD_ARG                     # pad > k/2
     assert library.gh_stem_space_to_depth(None, 1, 1, 1, 1, 1, 8, 8, None, 0, None) == _lib.GH_ERR_BAD_ARG
     assert library.gh_stem_space_to_depth(dummy, 1, 1, 1, 1, 1, 7, 8, dummy, 0, None) == _lib.GH_ERR_UNSUPPORTED             # odd H
+    three = ctypes.c_float * 3
+    mean, std = three(0.485, 0.456, 0.406), three(0.229, 0.224, 0.225)
+    assert library.gh_normalize_u8(None, None, 1, 3, 16, mean, std, None) == _lib.GH_ERR_BAD_ARG
+    assert library.gh_normalize_u8(dummy, dummy, 1, 3, 16, None, std, None) == _lib.GH_ERR_BAD_ARG
+    assert library.gh_normalize_u8(dummy, dummy, 0, 3, 16, mean, std, None) == _lib.GH_ERR_BAD_ARG                           # no images
+    assert library.gh_normalize_u8(dummy, dummy, 1, 5, 16, mean, std, None) == _lib.GH_ERR_UNSUPPORTED                       # > 4 channels
+    assert library.gh_normalize_u8(dummy, dummy, 1, 3, 16, mean, three(0.229, 0.0, 0.225), None) == _lib.GH_ERR_BAD_ARG      # zero std
 
 
 def test_option_validation_and_environment_hook(monkeypatch, library):
